@@ -1,0 +1,181 @@
+/*
+ * svk.h — C-ABI of libsvk.so, the sm_100a kernel library behind the speaker-embedding hot path.
+ *
+ * Drop-in boundary: the reference (ZihanLiao/pytorch-kaldi-resnet) has no native code;
+ * its hot path is `scripts/model.py` (NeuralSpeakerModel), `scripts/train_resnet.py` (train loop),
+ * `scripts/decode.py` (extraction) and `scripts/cosine_score.py` / `compute_topk_mean_std.py` /
+ * `adaptive_snorm.py` (scoring), all of which reach the GPU only through torch library calls.  Each entry
+ * point below replaces one of those torch calls; the citation after "replaces:" is the reference call site.
+ * The Python host side (pytorch-kaldi-resnet_b200/svk) binds these with ctypes.
+ *
+ * Conventions
+ *  - plain pointers + sizes only; every pointer is DEVICE memory owned by the caller (torch), contiguous.
+ *  - activations are NHWC ("channels last"); `dtype` selects their storage: SVK_F32 (validation mode) or
+ *    SVK_BF16 (product mode).  Accumulation is always fp32; cross-CTA statistics are fp64.
+ *  - `stream` is a cudaStream_t passed as void*.
+ *  - return 0 on success; negative SVK_E_* on bad arguments / unsupported shapes; positive = cudaError_t.
+ *    svk_last_error_string() describes the last failure on the calling thread.  There is no CPU fallback.
+ *  - kernels never allocate, free or retain pointers.
+ */
+#ifndef SVK_H_
+#define SVK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVK_VERSION 100
+
+enum { SVK_F32 = 0, SVK_BF16 = 1 };
+enum { SVK_IMPL_SIMT = 0, SVK_IMPL_TCGEN05 = 1 };
+enum {
+  SVK_E_BADARG = -1,      /* null pointer / non-positive size */
+  SVK_E_UNSUPPORTED = -2, /* shape, dtype or impl not supported by this kernel */
+  SVK_E_ALIGN = -3,       /* pointer or channel count not aligned as required */
+  SVK_E_DRIVER = -4       /* cuTensorMapEncodeTiled / driver entry point failure */
+};
+
+int svk_version(void);
+const char* svk_last_error_string(void);
+/* Number of kernels launched by this library in this process (for bench.py's gpu_launches). */
+long long svk_launch_count(void);
+
+/* ---------------------------------------------------------------- convolution ---------------------------- */
+/* One conv layer of the ResNet trunk.  replaces: nn.Conv2d forward/backward, model.py:12-15 (conv3x3),
+ * model.py:233-236 (1x1 stride-2 downsample).  Weights are pre-packed by svk_pack_conv_weight. */
+typedef struct svk_conv_desc {
+  int N, H, W, Cin;   /* input  NHWC */
+  int Ho, Wo, Cout;   /* output NHWC; Ho = (H-1)/stride+1 (pad = R/2) */
+  int R;              /* 1 or 3 (square filter, pad R/2) */
+  int stride;         /* 1 or 2 */
+  int dtype;          /* SVK_F32 | SVK_BF16 (activation + packed-weight storage) */
+  int impl;           /* SVK_IMPL_SIMT (any dtype) | SVK_IMPL_TCGEN05 (bf16 only) */
+} svk_conv_desc;
+
+/* OIHW fp32 master weights -> packed [R*R][Cout][Cin] (w_fwd, K-major for fprop) and
+ * [R*R][Cin][Cout] (w_dgrad), both in `dtype`.  Either output may be NULL. */
+int svk_pack_conv_weight(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int R,
+                         int dtype, void* stream);
+/* packed fp32 [R*R][Cout][Cin] weight gradient -> OIHW fp32 (overwrites dw_oihw). */
+int svk_unpack_conv_wgrad(const float* dw_packed, float* dw_oihw, int Cout, int Cin, int R, void* stream);
+
+/* y = conv(x, w).  Epilogue (all optional, applied in this order on the fp32 accumulator):
+ *   v = acc * scale[c] + shift[c]          (scale/shift both non-NULL: folded eval-mode BatchNorm)
+ *   v += residual[idx]                      (residual non-NULL, same NHWC shape as y)
+ *   v = max(v, 0)                           (relu != 0)
+ *   y[n, :, w >= valid_wo[n], :] = 0        (valid_wo non-NULL: per-utterance valid output width — batched
+ *                                            extraction keeps exact batch-1 semantics, decode.py:198)
+ *   stats[c] += sum(y), stats[Cout+c] += sum(y^2) over the stored (rounded) values   (stats non-NULL)
+ * replaces: model.py:51,55,59 (+ bn/relu/add at :52-62 in eval mode). */
+int svk_conv2d_fwd(const svk_conv_desc* d, const void* x, const void* w_fwd, void* y, double* stats,
+                   const float* scale, const float* shift, const void* residual, int relu,
+                   const int* valid_wo, void* stream);
+/* dx = conv_transpose(dy, w) [+ res] [+ res_m * (mask > 0)]  — data gradient; desc describes the FORWARD conv
+ * (dy is N,Ho,Wo,Cout; dx is N,H,W,Cin).  replaces: cuDNN dgrad under loss.backward(), train_resnet.py:327. */
+int svk_conv2d_dgrad(const svk_conv_desc* d, const void* dy, const void* w_dgrad, void* dx, const void* res,
+                     const void* res_m, const void* mask, void* stream);
+/* dw_packed[R*R][Cout][Cin] (fp32) += dy^T * im2col(x).  Caller zeroes dw_packed first (split-K uses atomics).
+ * replaces: cuDNN wgrad under loss.backward(), train_resnet.py:327. */
+int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream);
+
+/* Stem: 3x3 s1 p1 conv, Cin = 1, x is the (B,F,T) fp32 feature tensor itself.  replaces: model.py:247-249. */
+int svk_stem_conv_fwd(const float* x, const float* w /*[Cout][9]*/, void* y /*N,H,W,Cout*/, int N, int H, int W,
+                      int Cout, int dtype, const float* scale, const float* shift, int relu, void* stream);
+int svk_stem_conv_wgrad(const float* x, const void* dy, float* dw /*[Cout][9], overwritten*/, int N, int H, int W,
+                        int Cout, int dtype, void* stream);
+
+/* ---------------------------------------------------------------- BatchNorm2d ---------------------------- */
+/* stats[c] += sum_m x[m,c]; stats[C+c] += sum_m x[m,c]^2  (x is [M,C]).  Caller zeroes stats. */
+int svk_channel_stats(const void* x, long long M, int C, int dtype, double* stats, void* stream);
+/* Training-mode BN finalise. replaces: native_batch_norm statistics + running-stat update, model.py:52,56,250.
+ * mean = s1/M, var_b = s2/M - mean^2; scale = gamma*rstd, shift = beta - mean*scale; running stats updated with
+ * momentum and UNBIASED variance; save_mean/save_rstd kept for backward. */
+int svk_bn_finalize(const double* stats, long long M, int C, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                    float* save_mean, float* save_rstd, void* stream);
+/* Eval-mode BN coefficients from running stats: scale = gamma/sqrt(rv+eps), shift = beta - rm*scale. */
+int svk_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, int C, float* scale, float* shift, void* stream);
+/* out = act(scale*x + shift + R) with R = 0 | res | rscale*res + rshift.  replaces: model.py:52-53,56-62. */
+int svk_bn_act_fwd(const void* x, const float* scale, const float* shift, const void* res, const float* rscale,
+                   const float* rshift, int relu, void* out, long long M, int C, int dtype, void* stream);
+/* Backward reductions for one BN (optionally two sharing the same upstream gradient — main path + downsample):
+ * g = dout * (out > 0 if out else 1);  sums[0:C] += sum g;  sums[C:2C] += sum g*xhat(c,mean,rstd);
+ * sums[2C:3C] += sum g*xhat(c_b,mean_b,rstd_b) if c_b.  replaces: native_batch_norm_backward reductions. */
+int svk_bn_bwd_reduce(const void* dout, const void* out, const void* c, const float* mean, const float* rstd,
+                      const void* c_b, const float* mean_b, const float* rstd_b, double* sums, long long M, int C,
+                      int dtype, void* stream);
+/* dc = gamma*rstd*(g - s1/M - xhat*s2/M) (and dc_b likewise); dgamma = s2, dbeta = s1 written to fp32 grads. */
+int svk_bn_bwd_apply(const void* dout, const void* out, const void* c, const float* mean, const float* rstd,
+                     const float* gamma, void* dc, const void* c_b, const float* mean_b, const float* rstd_b,
+                     const float* gamma_b, void* dc_b, const double* sums, float* dgamma, float* dbeta,
+                     float* dgamma_b, float* dbeta_b, long long M, int C, int dtype, void* stream);
+/* out = a + b  |  out = a + b*(mask>0)  (elementwise, residual-gradient merge).  mask may be NULL. */
+int svk_add_masked(const void* a, const void* b, const void* mask, void* out, long long n, int dtype, void* stream);
+/* dx[n, 2i, 2j, :] += d[n, i, j, :]  (merge the 1x1/s2 downsample data gradient into the block-input gradient). */
+int svk_add_strided2(void* dx, const void* d, int N, int H, int W, int Ho, int Wo, int C, int dtype, void* stream);
+
+/* ---------------------------------------------------------------- pooling + FC --------------------------- */
+/* StatsPooling. mode 0 = 'mean' -> out[n, c*H + h]; mode 1 = 'mean+std' reproducing the reference's swapped
+ * var_mean unpack: out[n, c*2H + h] = unbiased var over time, out[n, c*2H + H + h] = sqrt(mean over time).
+ * valid_w (nullable) = per-utterance width.  replaces: model.py:441-455 (+ Flatten :381). */
+int svk_statspool_fwd(const void* x, float* out, int N, int H, int W, int C, int mode, const int* valid_w,
+                      int dtype, void* stream);
+int svk_statspool_bwd(const void* x, const float* dout, void* dx, int N, int H, int W, int C, int mode, int dtype,
+                      void* stream);
+/* C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] (+ bias[N]) (+ beta*C); fp32; element (m,k) of op(A) at
+ * A[m*a_sm + k*a_sk], element (k,n) of op(B) at B[k*b_sk + n*b_sn].
+ * replaces: nn.Linear fc1 (model.py:384) and its backward, F.linear in AAMLayer (model.py:485). */
+int svk_sgemm(const float* A, long long a_sm, long long a_sk, const float* B, long long b_sk, long long b_sn,
+              float* C, long long ldc, int M, int N, int K, float alpha, float beta, const float* bias,
+              void* stream);
+/* out[n] = sum_m x[m,n]  (bias gradient). */
+int svk_colsum(const float* x, float* out, int M, int N, void* stream);
+
+/* ---------------------------------------------------------------- AAM-softmax head ----------------------- */
+/* xhat = x / max(||x||, eps) row-wise; inv[r] = 1/max(||x||,eps).  replaces: F.normalize, model.py:485. */
+int svk_l2norm_rows_fwd(const float* x, float* xhat, float* inv, int rows, int cols, float eps, void* stream);
+/* dx = (dxhat - xhat * <xhat, dxhat>) * inv.  (exact for ||x|| > eps) */
+int svk_l2norm_rows_bwd(const float* dxhat, const float* xhat, const float* inv, float* dx, int rows, int cols,
+                        void* stream);
+/* In place on cos[B,C]: target column -> phi (cos(theta+m) with the monotonic fallback), everything * s.
+ * cos_t[b] keeps the raw target cosine for backward.  replaces: model.py:487-499. */
+int svk_aam_margin_fwd(float* cos_logits, const long long* label, float* cos_t, int B, int C, float cos_m,
+                       float sin_m, float th, float mm, float s, void* stream);
+/* In place on dlogits[B,C] -> dcos (chain rule through the margin and the scale). */
+int svk_aam_margin_bwd(float* dlogits, const long long* label, const float* cos_t, int B, int C, float cos_m,
+                       float sin_m, float th, float s, void* stream);
+/* Cross entropy (mean over batch). loss_rows[b] = lse_b - logits[b,y_b]; lse[b] saved; rank[b] = number of
+ * logits strictly greater than the target's (top-k correct iff rank < k).
+ * replaces: nn.CrossEntropyLoss (train_resnet.py:201,317), accuracy.py:4-16. */
+int svk_ce_fwd(const float* logits, const long long* label, float* loss_rows, float* lse, int* rank, int B, int C,
+               void* stream);
+/* dlogits = (softmax - onehot) * gscale  (gscale = upstream_grad / B). gscale is a DEVICE scalar. */
+int svk_ce_bwd(const float* logits, const long long* label, const float* lse, const float* gscale, float* dlogits,
+               int B, int C, void* stream);
+
+/* ---------------------------------------------------------------- optimiser ------------------------------ */
+/* torch.optim.SGD semantics on flat buffers: d = g*gscale + wd*p; buf = mom*buf + d; p -= lr*buf.
+ * (buf zero-initialised makes the first step equal torch's buf = d.)  replaces: train_resnet.py:203,328. */
+int svk_sgd_step(float* p, const float* g, float* buf, long long n, float lr, float momentum, float wd,
+                 float gscale, void* stream);
+int svk_cast(const void* src, void* dst, long long n, int src_dtype, int dst_dtype, void* stream);
+
+/* ---------------------------------------------------------------- scoring -------------------------------- */
+/* score[t] = cos(E[ie[t]] - mean, T[it[t]] - mean), eps 1e-8 on the norm product as F.cosine_similarity.
+ * replaces: cosine_score.py:60-65. */
+int svk_cosine_score_pairs(const float* E, const float* T, const float* mean, const int* ie, const int* it,
+                           float* score, long long ntrials, int D, void* stream);
+/* Per row of scores[rows, ncoh]: top-k values -> mean and UNBIASED std.  replaces: compute_topk_mean_std.py:17-19. */
+int svk_topk_meanstd(const float* scores, int rows, int ncoh, int topk, float* mean, float* stdv, void* stream);
+/* out[t] = 0.5*((s-me[ie])/max(se[ie],1e-8) + (s-mt[it])/max(st[it],1e-8)).  replaces: adaptive_snorm.py:33-34. */
+int svk_snorm_apply(const float* score, const int* ie, const int* it, const float* mean_e, const float* std_e,
+                    const float* mean_t, const float* std_t, float* out, long long ntrials, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVK_H_ */

@@ -1,0 +1,418 @@
+// CUDA-core implicit-GEMM convolution (fprop / dgrad / wgrad), fp32 accumulate, fp32 or bf16 storage.
+// This is the fp32 VALIDATION-mode path (north-star: "<=1e-4 relative in an fp32 validation mode") and the
+// on-device cross-check for the tcgen05 kernels in conv_tc.cu; it is not the product path for bf16.
+#include "svk_common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+struct GatherArgs {
+  const void* in;    // fprop: x [N,Hin,Win,Kc]; dgrad: dy [N,Hin,Win,Kc]
+  const void* w;     // packed [taps][Nout][Kc]
+  void* out;         // [N,Hout,Wout,Nout]
+  int N, Hin, Win, Kc, Hout, Wout, Nout, R, stride;
+  const float* scale; const float* shift;
+  const void* res; const void* res_m; const void* mask;
+  int relu;
+  const int* valid_w;
+};
+
+template <typename T> __device__ inline void load4(const T* p, float (&v)[4]);
+template <> __device__ inline void load4<float>(const float* p, float (&v)[4]) {
+  float4 r = *reinterpret_cast<const float4*>(p); v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+template <> __device__ inline void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <typename T> __device__ inline void store4(T* p, const float (&v)[4]);
+template <> __device__ inline void store4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ inline void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+  h[0] = __floats2bfloat162_rn(v[0], v[1]); h[1] = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+// out[m, n] = sum_{tap, k} in[pix(m, tap), k] * w[tap][n][k]
+template <typename T, bool DGRAD>
+__global__ void __launch_bounds__(NT) conv_gather_kernel(GatherArgs a) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const T* in = (const T*)a.in;
+  const T* w = (const T*)a.w;
+  const int t = threadIdx.x;
+  const long long Mtot = (long long)a.N * a.Hout * a.Wout;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int pad = a.R / 2;
+  // this thread's load row
+  const int lrow = t >> 2, lk = (t & 3) * 4;
+  long long lm = m0 + lrow;
+  bool lvalid = lm < Mtot;
+  int ln = 0, loh = 0, low = 0;
+  if (lvalid) { low = (int)(lm % a.Wout); long long q = lm / a.Wout; loh = (int)(q % a.Hout); ln = (int)(q / a.Hout); }
+  const int bn = n0 + lrow;  // weight row this thread loads
+  const bool bvalid = bn < a.Nout;
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int r = 0; r < a.R; ++r) {
+    for (int s = 0; s < a.R; ++s) {
+      int ih, iw; bool ok = lvalid;
+      if (!DGRAD) {
+        ih = loh * a.stride + r - pad; iw = low * a.stride + s - pad;
+      } else {
+        int th = loh + pad - r, tw = low + pad - s;
+        ok = ok && th >= 0 && tw >= 0 && (th % a.stride == 0) && (tw % a.stride == 0);
+        ih = th / a.stride; iw = tw / a.stride;
+      }
+      ok = ok && ih >= 0 && ih < a.Hin && iw >= 0 && iw < a.Win;
+      const T* ap = in + (((long long)ln * a.Hin + ih) * a.Win + iw) * a.Kc;
+      const T* bp = w + ((long long)(r * a.R + s) * a.Nout + bn) * a.Kc;
+      for (int k0 = 0; k0 < a.Kc; k0 += BK) {
+        float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ok) load4<T>(ap + k0 + lk, av);
+        if (bvalid) load4<T>(bp + k0 + lk, bv);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { As[lk + i][lrow] = av[i]; Bs[lk + i][lrow] = bv[i]; }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+          float4 x = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+          float4 y = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+          const float xa[4] = {x.x, x.y, x.z, x.w}, ya[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ya[j], acc[i][j]);
+        }
+      }
+    }
+  }
+  // epilogue
+  const int n = n0 + tx * 4;
+  if (n >= a.Nout) return;
+  T* out = (T*)a.out;
+  float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+  if (a.scale) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sc[j] = a.scale[n + j]; sh[j] = a.shift[n + j]; }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + ty * 4 + i;
+    if (m >= Mtot) continue;
+    long long idx = m * a.Nout + n;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaf(acc[i][j], sc[j], sh[j]);
+    if (a.res) { float r4[4]; load4<T>((const T*)a.res + idx, r4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += r4[j]; }
+    if (a.res_m) { float r4[4], k4[4]; load4<T>((const T*)a.res_m + idx, r4); load4<T>((const T*)a.mask + idx, k4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += (k4[j] > 0.f) ? r4[j] : 0.f; }
+    if (a.relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f); }
+    if (a.valid_w) {
+      int ow = (int)(m % a.Wout); int nimg = (int)(m / ((long long)a.Wout * a.Hout));
+      if (ow >= a.valid_w[nimg]) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+    }
+    store4<T>(out + idx, v);
+  }
+}
+
+struct WgradArgs {
+  const void* x; const void* dy; float* dw;
+  int N, H, W, Cin, Ho, Wo, Cout, R, stride;
+  long long kslice;  // pixels per z-slice
+};
+
+// dw[tap][co][ci] += sum_pix dy[pix, co] * x[shift_tap(pix), ci]
+template <typename T>
+__global__ void __launch_bounds__(NT) conv_wgrad_simt_kernel(WgradArgs a) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const T* x = (const T*)a.x;
+  const T* dy = (const T*)a.dy;
+  const int t = threadIdx.x;
+  const int co0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;            // column = tap*Cin + ci
+  const int ncols = a.R * a.R * a.Cin;
+  const long long Ktot = (long long)a.N * a.Ho * a.Wo;
+  const long long kbeg = (long long)blockIdx.z * a.kslice;
+  long long kend = kbeg + a.kslice; if (kend > Ktot) kend = Ktot;
+  const int pad = a.R / 2;
+  const int lkk = t >> 4, l4 = (t & 15) * 4;
+  const bool avalid = co0 + l4 < a.Cout;
+  const int col = n0 + l4;
+  const bool bvalid = col < ncols;
+  int tap = 0, ci = 0, r = 0, s = 0;
+  if (bvalid) { tap = col / a.Cin; ci = col % a.Cin; r = tap / a.R; s = tap % a.R; }
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long k0 = kbeg; k0 < kend; k0 += BK) {
+    long long k = k0 + lkk;
+    float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k < kend) {
+      if (avalid) load4<T>(dy + k * a.Cout + co0 + l4, av);
+      if (bvalid) {
+        int ow = (int)(k % a.Wo); long long q = k / a.Wo; int oh = (int)(q % a.Ho); int n = (int)(q / a.Ho);
+        int ih = oh * a.stride + r - pad, iw = ow * a.stride + s - pad;
+        if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W)
+          load4<T>(x + (((long long)n * a.H + ih) * a.W + iw) * a.Cin + ci, bv);
+      }
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[lkk][l4]) = make_float4(av[0], av[1], av[2], av[3]);
+    *reinterpret_cast<float4*>(&Bs[lkk][l4]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 xa4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 ya4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float xa[4] = {xa4.x, xa4.y, xa4.z, xa4.w}, ya[4] = {ya4.x, ya4.y, ya4.z, ya4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ya[j], acc[i][j]);
+    }
+  }
+  const int c = n0 + tx * 4;
+  if (c >= ncols) return;
+  const int otap = c / a.Cin, oci = c % a.Cin;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int co = co0 + ty * 4 + i;
+    if (co >= a.Cout) continue;
+    float* dst = a.dw + ((long long)otap * a.Cout + co) * a.Cin + oci;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(dst + j, acc[i][j]);
+  }
+}
+
+}  // namespace
+
+static int check_desc(const char* name, const svk_conv_desc* d) {
+  SVK_REQUIRE(d, SVK_E_BADARG, "%s: null desc", name);
+  SVK_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, SVK_E_BADARG, "%s: non-positive dims", name);
+  SVK_REQUIRE((d->R == 1 || d->R == 3) && (d->stride == 1 || d->stride == 2), SVK_E_UNSUPPORTED,
+              "%s: R=%d stride=%d unsupported", name, d->R, d->stride);
+  SVK_REQUIRE(d->Ho == (d->H - 1) / d->stride + 1 && d->Wo == (d->W - 1) / d->stride + 1, SVK_E_BADARG,
+              "%s: Ho/Wo inconsistent with H/W/stride", name);
+  SVK_REQUIRE(d->Cin % 16 == 0 && d->Cout % 16 == 0, SVK_E_UNSUPPORTED, "%s: channels must be multiples of 16", name);
+  return 0;
+}
+
+int svk_conv2d_fwd_simt(const svk_conv_desc* d, const void* x, const void* w, void* y, const float* scale,
+                        const float* shift, const void* residual, int relu, const int* valid_wo, cudaStream_t st) {
+  GatherArgs a{x, w, y, d->N, d->H, d->W, d->Cin, d->Ho, d->Wo, d->Cout, d->R, d->stride, scale, shift, residual,
+               nullptr, nullptr, relu, valid_wo};
+  long long M = (long long)d->N * d->Ho * d->Wo;
+  dim3 grid((unsigned)((M + BM - 1) / BM), (d->Cout + BN - 1) / BN);
+  if (d->dtype == SVK_F32) conv_gather_kernel<float, false><<<grid, NT, 0, st>>>(a);
+  else conv_gather_kernel<__nv_bfloat16, false><<<grid, NT, 0, st>>>(a);
+  SVK_LAUNCH_CHECK("conv2d_fwd(simt)");
+  return 0;
+}
+int svk_conv2d_dgrad_simt(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
+                          const void* res_m, const void* mask, cudaStream_t st) {
+  GatherArgs a{dy, w, dx, d->N, d->Ho, d->Wo, d->Cout, d->H, d->W, d->Cin, d->R, d->stride, nullptr, nullptr, res,
+               res_m, mask, 0, nullptr};
+  long long M = (long long)d->N * d->H * d->W;
+  dim3 grid((unsigned)((M + BM - 1) / BM), (d->Cin + BN - 1) / BN);
+  if (d->dtype == SVK_F32) conv_gather_kernel<float, true><<<grid, NT, 0, st>>>(a);
+  else conv_gather_kernel<__nv_bfloat16, true><<<grid, NT, 0, st>>>(a);
+  SVK_LAUNCH_CHECK("conv2d_dgrad(simt)");
+  return 0;
+}
+int svk_conv2d_wgrad_simt(const svk_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  WgradArgs a{x, dy, dw, d->N, d->H, d->W, d->Cin, d->Ho, d->Wo, d->Cout, d->R, d->stride, 0};
+  int gx = (d->Cout + BM - 1) / BM, gy = (d->R * d->R * d->Cin + BN - 1) / BN;
+  long long K = (long long)d->N * d->Ho * d->Wo;
+  long long want = (long long)svk_num_sms() * 4 / ((long long)gx * gy) + 1;   // ~4 CTAs per SM in total
+  long long maxsl = (K + 255) / 256;                                          // at least 256 pixels per slice
+  if (want > maxsl) want = maxsl;
+  if (want < 1) want = 1;
+  if (want > 65535) want = 65535;
+  long long ks = (K + want - 1) / want;
+  ks = (ks + BK - 1) / BK * BK;
+  a.kslice = ks;
+  int gz = (int)((K + ks - 1) / ks);
+  dim3 grid(gx, gy, gz);
+  if (d->dtype == SVK_F32) conv_wgrad_simt_kernel<float><<<grid, NT, 0, st>>>(a);
+  else conv_wgrad_simt_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(a);
+  SVK_LAUNCH_CHECK("conv2d_wgrad(simt)");
+  return 0;
+}
+
+// implemented in conv_tc.cu
+int svk_conv2d_fwd_tc(const svk_conv_desc* d, const void* x, const void* w, void* y, double* stats, const float* scale,
+                      const float* shift, const void* residual, int relu, const int* valid_wo, cudaStream_t st);
+int svk_conv2d_dgrad_tc(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
+                        const void* res_m, const void* mask, cudaStream_t st);
+int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st);
+
+SVK_API int svk_conv2d_fwd(const svk_conv_desc* d, const void* x, const void* w, void* y, double* stats,
+                           const float* scale, const float* shift, const void* residual, int relu,
+                           const int* valid_wo, void* stream) {
+  if (int e = check_desc("conv2d_fwd", d)) return e;
+  SVK_REQUIRE(x && w && y, SVK_E_BADARG, "conv2d_fwd: null pointer");
+  SVK_REQUIRE((scale == nullptr) == (shift == nullptr), SVK_E_BADARG, "conv2d_fwd: scale and shift go together");
+  SVK_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && (!residual || aligned16(residual)), SVK_E_ALIGN,
+              "conv2d_fwd: pointers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  if (d->impl == SVK_IMPL_TCGEN05) {
+    SVK_REQUIRE(d->dtype == SVK_BF16, SVK_E_UNSUPPORTED, "conv2d_fwd: tcgen05 path is bf16 only");
+    return svk_conv2d_fwd_tc(d, x, w, y, stats, scale, shift, residual, relu, valid_wo, st);
+  }
+  SVK_REQUIRE(d->impl == SVK_IMPL_SIMT, SVK_E_BADARG, "conv2d_fwd: bad impl %d", d->impl);
+  if (int e = svk_conv2d_fwd_simt(d, x, w, y, scale, shift, residual, relu, valid_wo, st)) return e;
+  if (stats) return svk_channel_stats(y, (long long)d->N * d->Ho * d->Wo, d->Cout, d->dtype, stats, stream);
+  return 0;
+}
+
+SVK_API int svk_conv2d_dgrad(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
+                             const void* res_m, const void* mask, void* stream) {
+  if (int e = check_desc("conv2d_dgrad", d)) return e;
+  SVK_REQUIRE(dy && w && dx, SVK_E_BADARG, "conv2d_dgrad: null pointer");
+  SVK_REQUIRE((res_m == nullptr) == (mask == nullptr), SVK_E_BADARG, "conv2d_dgrad: res_m and mask go together");
+  cudaStream_t st = as_stream(stream);
+  if (d->impl == SVK_IMPL_TCGEN05) {
+    SVK_REQUIRE(d->dtype == SVK_BF16, SVK_E_UNSUPPORTED, "conv2d_dgrad: tcgen05 path is bf16 only");
+    return svk_conv2d_dgrad_tc(d, dy, w, dx, res, res_m, mask, st);
+  }
+  SVK_REQUIRE(d->impl == SVK_IMPL_SIMT, SVK_E_BADARG, "conv2d_dgrad: bad impl %d", d->impl);
+  return svk_conv2d_dgrad_simt(d, dy, w, dx, res, res_m, mask, st);
+}
+
+SVK_API int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
+  if (int e = check_desc("conv2d_wgrad", d)) return e;
+  SVK_REQUIRE(x && dy && dw, SVK_E_BADARG, "conv2d_wgrad: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (d->impl == SVK_IMPL_TCGEN05) {
+    SVK_REQUIRE(d->dtype == SVK_BF16, SVK_E_UNSUPPORTED, "conv2d_wgrad: tcgen05 path is bf16 only");
+    return svk_conv2d_wgrad_tc(d, x, dy, dw, st);
+  }
+  SVK_REQUIRE(d->impl == SVK_IMPL_SIMT, SVK_E_BADARG, "conv2d_wgrad: bad impl %d", d->impl);
+  return svk_conv2d_wgrad_simt(d, x, dy, dw, st);
+}
+
+// ------------------------------------------------------------------------------------------------ stem (Cin = 1)
+// One thread per output pixel, all Cout (<= 64) channels in registers; HBM-bound: reads 4 B, writes 2*Cout B per pixel.
+template <typename T, int CO>
+__global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       T* __restrict__ y, int N, int H, int W,
+                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       int relu) {
+  __shared__ float ws[CO * 9], ss[CO], sb[CO];
+  for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < CO; i += blockDim.x) { ss[i] = scale ? scale[i] : 1.f; sb[i] = shift ? shift[i] : 0.f; }
+  __syncthreads();
+  long long total = (long long)N * H * W;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    int wq = (int)(p % W); long long q = p / W; int h = (int)(q % H);
+    float v[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int ih = h + r - 1, iw = wq + s - 1;
+        v[r * 3 + s] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? x[p + (long long)(r - 1) * W + (s - 1)] : 0.f;
+      }
+    T* dst = y + p * CO;
+    constexpr int V = Vec<T>::N;
+#pragma unroll
+    for (int c0 = 0; c0 < CO; c0 += V) {
+      float o[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc = fmaf(v[k], ws[(c0 + j) * 9 + k], acc);
+        acc = fmaf(acc, ss[c0 + j], sb[c0 + j]);
+        o[j] = relu ? fmaxf(acc, 0.f) : acc;
+      }
+      Vec<T>::store(dst + c0, o);
+    }
+  }
+}
+SVK_API int svk_stem_conv_fwd(const float* x, const float* w, void* y, int N, int H, int W, int Cout, int dtype,
+                              const float* scale, const float* shift, int relu, void* stream) {
+  SVK_REQUIRE(x && w && y && N > 0 && H > 0 && W > 0, SVK_E_BADARG, "stem_conv_fwd: bad args");
+  SVK_REQUIRE(Cout == 32 || Cout == 64, SVK_E_UNSUPPORTED, "stem_conv_fwd: Cout must be 32 or 64, got %d", Cout);
+  SVK_REQUIRE((scale == nullptr) == (shift == nullptr), SVK_E_BADARG, "stem_conv_fwd: scale and shift go together");
+  long long total = (long long)N * H * W;
+  long long b = (total + 127) / 128; long long cap = (long long)svk_num_sms() * 16; if (b > cap) b = cap;
+  cudaStream_t st = as_stream(stream);
+  SVK_DISPATCH_DTYPE(dtype, "stem_conv_fwd",
+    if (Cout == 32) stem_fwd_kernel<T, 32><<<(int)b, 128, 0, st>>>(x, w, (T*)y, N, H, W, scale, shift, relu);
+    else stem_fwd_kernel<T, 64><<<(int)b, 128, 0, st>>>(x, w, (T*)y, N, H, W, scale, shift, relu);)
+  SVK_LAUNCH_CHECK("stem_conv_fwd");
+  return 0;
+}
+
+// dw[co][tap] = sum_p dy[p, co] * x[p + shift(tap)].  Block = (CO channels) x (256/CO pixel lanes); per-block partials
+// are combined with fp32 atomics into dw (zeroed here first by a memset node).
+template <typename T>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                                         float* __restrict__ dw, int N, int H, int W, int CO) {
+  const int c = threadIdx.x % CO, lane_p = threadIdx.x / CO, lanes = blockDim.x / CO;
+  long long total = (long long)N * H * W;
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  for (long long p = (long long)blockIdx.x * lanes + lane_p; p < total; p += (long long)gridDim.x * lanes) {
+    int wq = (int)(p % W); long long q = p / W; int h = (int)(q % H);
+    float g = to_f(dy[p * CO + c]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int ih = h + r - 1, iw = wq + s - 1;
+        float xv = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? x[p + (long long)(r - 1) * W + (s - 1)] : 0.f;
+        acc[r * 3 + s] = fmaf(g, xv, acc[r * 3 + s]);
+      }
+  }
+  __shared__ float red[256 * 9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) red[threadIdx.x * 9 + k] = acc[k];
+  __syncthreads();
+  for (int o = threadIdx.x; o < CO * 9; o += blockDim.x) {
+    int cc = o / 9, k = o % 9;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[(l * CO + cc) * 9 + k];
+    atomicAdd(&dw[o], s);
+  }
+}
+SVK_API int svk_stem_conv_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout, int dtype,
+                                void* stream) {
+  SVK_REQUIRE(x && dy && dw && N > 0 && H > 0 && W > 0, SVK_E_BADARG, "stem_conv_wgrad: bad args");
+  SVK_REQUIRE(Cout == 32 || Cout == 64, SVK_E_UNSUPPORTED, "stem_conv_wgrad: Cout must be 32 or 64, got %d", Cout);
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * Cout * 9, st);
+  SVK_REQUIRE(e == cudaSuccess, (int)e, "stem_conv_wgrad: memset failed: %s", cudaGetErrorString(e));
+  long long total = (long long)N * H * W;
+  int lanes = 256 / Cout;
+  long long b = (total + lanes * 16 - 1) / (lanes * 16); long long cap = (long long)svk_num_sms() * 4; if (b > cap) b = cap; if (b < 1) b = 1;
+  SVK_DISPATCH_DTYPE(dtype, "stem_conv_wgrad",
+    stem_wgrad_kernel<T><<<(int)b, 256, 0, st>>>(x, (const T*)dy, dw, N, H, W, Cout);)
+  SVK_LAUNCH_CHECK("stem_conv_wgrad");
+  return 0;
+}

@@ -1,0 +1,725 @@
+// bf16 implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands staged by TMA.
+//
+//   fprop / dgrad  ("gather GEMM"):  D[128 pixels x BN channels] += A[128 pixels x KC] * B[BN x KC]^T   per (tap, k-chunk)
+//       A = a bh x bw box of NHWC pixels shifted by the tap offset, fetched by ONE 4-D TMA box; out-of-image
+//           coordinates are zero-filled by TMA (= the conv padding), stride-2 uses TMA element strides.
+//       B = packed weights [tap][Nout][Kc] (K-major), one 2-D TMA box.
+//       Both land in 128B/64B-swizzled K-major smem and feed tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16)
+//       with fp32 accumulators in TMEM (double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
+//       Epilogue (4 warps): tcgen05.ld -> scale/shift -> +residual -> ReLU -> bf16 -> global, plus per-channel
+//       sum / sum-of-squares of the stored values (BatchNorm batch statistics) reduced through smem.
+//   wgrad:  D_tap[Cout x Cin_blk] += dy_tile^T[Cout x P] * x_tap_tile[P x Cin_blk], P = pixels of a tile (K dim).
+//       Both operands are "MN-major" (channels contiguous): the same NHWC TMA boxes, UMMA descriptors with the
+//       transpose bits set.  One TMEM accumulator region per filter tap; split-K over pixel tiles across CTAs, fp32
+//       atomics into the packed gradient.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
+// Every mbarrier wait is bounded (trap after ~4 s) so a protocol bug cannot hang the GPU.
+#include "svk_common.cuh"
+#include <cuda.h>
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz: protocol bug, do not hang the device
+      printf("svk conv_tc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
+// a_major bit15, b_major bit16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------ fprop / dgrad kernel
+struct GatherP {
+  int Hc, Wc;                 // output class-grid (tile space)
+  int bh, bw, tiles_h, tiles_w, num_pix_tiles, n_blocks, total_tiles;
+  int in_mul;                 // input coordinate = class coordinate * in_mul + tap offset
+  int ntaps;
+  int tap_dh[9], tap_dw[9], tap_w[9];
+  int kchunks;                // Kc / KC
+  int Nout;                   // output channels (row pitch of out)
+  int Hout, Wout, o_mul, o_off_h, o_off_w;   // out pixel = (i*o_mul + o_off_h, j*o_mul + o_off_w)
+  bf16* out;
+  const float* scale; const float* shift;
+  const bf16* res; const bf16* res_m; const bf16* mask;
+  int relu;
+  const int* valid_w;
+  double* stats;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int SMEM_AUX = 1024;                 // barriers + tmem pointer
+constexpr int SCR_BYTES = 4 * 32 * 33 * 4;     // per-epilogue-warp transpose scratch
+constexpr int COEF_BYTES = 2 * 512 * 4;        // scale/shift staged in smem (Nout <= 512)
+
+template <int KC, int BN>
+struct GatherCfg {
+  static constexpr int ROWB = KC * 2;
+  static constexpr int A_BYTES = 128 * ROWB;
+  static constexpr int B_BYTES = BN * ROWB;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (180 * 1024) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);   // power of two for BN in {32,64,128,256}
+  static constexpr int SMEM = STAGES * STAGE + SMEM_AUX + SCR_BYTES + COEF_BYTES + 1024;
+  static constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
+  static constexpr uint32_t SBO = 8 * ROWB;
+};
+
+template <int KC, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ GatherP p) {
+  typedef GatherCfg<KC, BN> Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t stage0 = base;
+  const uint32_t aux = base + Cfg::STAGES * Cfg::STAGE;
+  // aux layout: full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @144, tmem ptr @160
+  const uint32_t bar_full = aux, bar_empty = aux + 64, bar_tfull = aux + 128, bar_tempty = aux + 144;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + Cfg::STAGES * Cfg::STAGE + 160);
+  float* scr = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE + SMEM_AUX);
+  float* coef = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE + SMEM_AUX + SCR_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (p.scale) {
+    for (int i = threadIdx.x; i < p.Nout; i += TC_THREADS) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int ksteps = p.ntaps * p.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t ph = 0;
+      const uint32_t a_bytes = (uint32_t)(p.bh * p.bw) * Cfg::ROWB;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nblk = tile % p.n_blocks;
+        int pt = tile / p.n_blocks;
+        const int tw = pt % p.tiles_w; pt /= p.tiles_w;
+        const int th = pt % p.tiles_h;
+        const int n = pt / p.tiles_h;
+        const int h0 = th * p.bh * p.in_mul, w0 = tw * p.bw * p.in_mul;
+        for (int t = 0; t < p.ntaps; ++t) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
+            const uint32_t sa = stage0 + stage * Cfg::STAGE;
+            mbar_expect_tx(bar_full + 8 * stage, a_bytes + Cfg::B_BYTES);
+            tma_load_4d(sa, &tmA, bar_full + 8 * stage, kc * KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n);
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full + 8 * stage, kc * KC, p.tap_w[t] * p.Nout + nblk * BN);
+            if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      int stage = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(bar_full + 8 * stage, ph);
+          tc_fence_after();
+          const uint32_t sa = stage0 + stage * Cfg::STAGE;
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            const uint64_t ad = make_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+            const uint64_t bd = make_desc(sa + Cfg::A_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+            tc_mma(d_tmem, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    float* myscr = scr + (warp - 2) * 32 * 33;
+    constexpr int NCH = BN / 32;
+    float s1[NCH], s2[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+    int stat_blk = -1;
+    int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nblk = tile % p.n_blocks;
+      int pt = tile / p.n_blocks;
+      const int tw = pt % p.tiles_w; pt /= p.tiles_w;
+      const int th = pt % p.tiles_h;
+      const int n = pt / p.tiles_h;
+      if (p.stats && stat_blk != nblk) {
+        if (stat_blk >= 0) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            atomicAdd(&p.stats[stat_blk * BN + c * 32 + lane], (double)s1[c]);
+            atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + lane], (double)s2[c]);
+            s1[c] = 0.f; s2[c] = 0.f;
+          }
+        }
+        stat_blk = nblk;
+      }
+      const int m = q * 32 + lane;          // accumulator row = pixel index inside the tile
+      const int i = m / p.bw, j = m - i * p.bw;
+      const int hc = th * p.bh + i, wc = tw * p.bw + j;
+      bool valid = (i < p.bh) && (hc < p.Hc) && (wc < p.Wc);
+      const int oh = hc * p.o_mul + p.o_off_h, ow = wc * p.o_mul + p.o_off_w;
+      const long long off = valid ? ((((long long)n * p.Hout + oh) * p.Wout + ow) * p.Nout + nblk * BN) : 0;
+      bool zero_out = false;
+      if (valid && p.valid_w) zero_out = ow >= p.valid_w[n];
+
+      mbar_wait(bar_tfull + 8 * acc, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t r[32];
+        tc_ld32(taddr + c * 32, r);
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+        if (p.scale) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaf(v[e], coef[nblk * BN + c * 32 + e], coef[512 + nblk * BN + c * 32 + e]);
+        }
+        if (valid) {
+          if (p.res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float t8[8];
+              Vec<bf16>::load(p.res + off + c * 32 + g * 8, t8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[g * 8 + e] += t8[e];
+            }
+          }
+          if (p.res_m) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float t8[8], k8[8];
+              Vec<bf16>::load(p.res_m + off + c * 32 + g * 8, t8);
+              Vec<bf16>::load(p.mask + off + c * 32 + g * 8, k8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[g * 8 + e] += (k8[e] > 0.f) ? t8[e] : 0.f;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+        if (zero_out) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0.f;
+        }
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float t8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t8[e] = v[g * 8 + e];
+            Vec<bf16>::store(p.out + off + c * 32 + g * 8, t8);
+          }
+        }
+        if (p.stats) {
+          // statistics of the values as stored (bf16-rounded); transpose through smem so lane e owns channel e
+#pragma unroll
+          for (int e = 0; e < 32; ++e) myscr[lane * 33 + e] = valid ? round_to<bf16>(v[e]) : 0.f;
+          __syncwarp();
+          float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) { float x = myscr[rr * 33 + lane]; a1 += x; a2 = fmaf(x, x, a2); }
+          s1[c] += a1; s2[c] += a2;
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; aph ^= 1u; }
+    }
+    if (p.stats && stat_blk >= 0) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        atomicAdd(&p.stats[stat_blk * BN + c * 32 + lane], (double)s1[c]);
+        atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + lane], (double)s2[c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ wgrad kernel
+struct WgradP {
+  int bh, bw, P;              // pixel tile; P = bh*bw (multiple of 16) = K extent of one tile
+  int tiles_h, tiles_w, num_pix_tiles;
+  int stride;                 // forward conv stride (input coord = out coord * stride + tap offset)
+  int R;
+  int Cin, Cout;
+  int cin_blk, n_cin_blk, n_m_blk, n_tap_grp, taps_per_grp, ntaps;
+  int ksplit;                 // CTAs per (m_blk, cin_blk, tap group)
+  float* dw;                  // packed [taps][Cout][Cin] fp32
+};
+
+constexpr int WG_B_STAGES = 3;
+
+// CK = channels per swizzle atom row: 64 (SW128) when both Cin and Cout are multiples of 64, else 32 (SW64).
+template <int CK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                     const __grid_constant__ WgradP p) {
+  constexpr int ROWB = CK * 2;
+  constexpr uint32_t LAYOUT = (CK == 64) ? 2u : 4u;
+  constexpr uint32_t SBO = 8 * ROWB;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int m_chunks = 128 / CK;                       // dy atoms fetched per tile (only those < Cout are real)
+  const int a_real = (p.Cout < 128 ? p.Cout : 128) / CK;
+  const int b_chunks = p.cin_blk / CK;
+  const uint32_t atom_bytes = (uint32_t)p.P * ROWB;    // one CK-channel chunk of a pixel tile
+  const uint32_t A_BYTES = atom_bytes * m_chunks;
+  const uint32_t B_BYTES = atom_bytes * b_chunks;
+  const uint32_t a0 = base;                            // 2 A slots
+  const uint32_t b0 = base + 2 * A_BYTES;              // WG_B_STAGES B slots
+  const uint32_t auxoff = 2 * A_BYTES + WG_B_STAGES * B_BYTES;
+  const uint32_t aux = base + auxoff;
+  const uint32_t bar_afull = aux, bar_aempty = aux + 16, bar_bfull = aux + 32, bar_bempty = aux + 64, bar_done = aux + 96;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + auxoff + 128);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < WG_B_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // work item
+  int wi = blockIdx.x;
+  const int ks = wi % p.ksplit; wi /= p.ksplit;
+  const int tg = wi % p.n_tap_grp; wi /= p.n_tap_grp;
+  const int cb = wi % p.n_cin_blk;
+  const int mb = wi / p.n_cin_blk;
+  const int tap0 = tg * p.taps_per_grp;
+  const int ntap = (p.ntaps - tap0) < p.taps_per_grp ? (p.ntaps - tap0) : p.taps_per_grp;
+  const int tiles_per = (p.num_pix_tiles + p.ksplit - 1) / p.ksplit;
+  const int t_beg = ks * tiles_per;
+  const int t_end = (t_beg + tiles_per) < p.num_pix_tiles ? (t_beg + tiles_per) : p.num_pix_tiles;
+  const int pad = p.R / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int bs = 0; uint32_t bph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int tile = t_beg; tile < t_end; ++tile) {
+        int pt = tile;
+        const int tw = pt % p.tiles_w; pt /= p.tiles_w;
+        const int th = pt % p.tiles_h;
+        const int n = pt / p.tiles_h;
+        const int h0 = th * p.bh, w0 = tw * p.bw;
+        mbar_wait(bar_aempty + 8 * as, aph ^ 1u);
+        mbar_expect_tx(bar_afull + 8 * as, atom_bytes * a_real);
+        for (int c = 0; c < a_real; ++c)
+          tma_load_4d(a0 + as * A_BYTES + c * atom_bytes, &tmDy, bar_afull + 8 * as, mb * 128 + c * CK, w0, h0, n);
+        if (++as == 2) { as = 0; aph ^= 1u; }
+        for (int t = 0; t < ntap; ++t) {
+          const int tap = tap0 + t;
+          const int r = tap / p.R, s = tap % p.R;
+          mbar_wait(bar_bempty + 8 * bs, bph ^ 1u);
+          mbar_expect_tx(bar_bfull + 8 * bs, B_BYTES);
+          for (int c = 0; c < b_chunks; ++c)
+            tma_load_4d(b0 + bs * B_BYTES + c * atom_bytes, &tmX, bar_bfull + 8 * bs, cb * p.cin_blk + c * CK,
+                        w0 * p.stride + s - pad, h0 * p.stride + r - pad, n);
+          if (++bs == WG_B_STAGES) { bs = 0; bph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, p.cin_blk, 1, 1);
+      int bs = 0; uint32_t bph = 0;
+      int as = 0; uint32_t aph = 0;
+      const int ksteps = p.P / 16;
+      for (int tile = t_beg; tile < t_end; ++tile) {
+        mbar_wait(bar_afull + 8 * as, aph);
+        tc_fence_after();
+        for (int t = 0; t < ntap; ++t) {
+          mbar_wait(bar_bfull + 8 * bs, bph);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.cin_blk);
+          for (int k = 0; k < ksteps; ++k) {
+            // MN-major: LBO = stride between CK-channel atoms, SBO = stride between 8-pixel groups; K advances by
+            // 16 pixel rows = 16*ROWB bytes (a whole number of swizzle atoms).
+            const uint64_t ad = make_desc(a0 + as * A_BYTES + k * 16 * ROWB, atom_bytes, SBO, LAYOUT);
+            const uint64_t bd = make_desc(b0 + bs * B_BYTES + k * 16 * ROWB, atom_bytes, SBO, LAYOUT);
+            tc_mma(d_tmem, ad, bd, idesc, (tile != t_beg || k != 0) ? 1u : 0u);
+          }
+          tc_commit(bar_bempty + 8 * bs);
+          if (++bs == WG_B_STAGES) { bs = 0; bph ^= 1u; }
+        }
+        tc_commit(bar_aempty + 8 * as);
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+      tc_commit(bar_done);
+    }
+  } else {
+    if (t_beg < t_end) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int co = mb * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int t = 0; t < ntap; ++t) {
+        for (int c = 0; c < p.cin_blk / 32; ++c) {
+          uint32_t r[32];
+          tc_ld32(taddr + t * p.cin_blk + c * 32, r);
+          if (co < p.Cout) {
+            float* dst = p.dw + ((long long)(tap0 + t) * p.Cout + co) * p.Cin + cb * p.cin_blk + c * 32;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(r[e]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 4-D map over an NHWC bf16 tensor; box = {ck channels, bw*es, bh*es, 1}, element strides {1, es, es, 1}.
+int make_nhwc_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int ck, int bw, int bh, int es) {
+  EncodeTiledFn enc = get_encode();
+  SVK_REQUIRE(enc, SVK_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)ck, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  SVK_REQUIRE(box[1] <= 256 && box[2] <= 256, SVK_E_UNSUPPORTED, "conv_tc: TMA box %ux%u too large", box[1], box[2]);
+  CUtensorMapSwizzle sw = (ck == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SVK_REQUIRE(r == CUDA_SUCCESS, SVK_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled(NHWC) failed with %d", (int)r);
+  return 0;
+}
+// 2-D map over packed weights [rows][K] bf16; box = {ck, bn}.
+int make_w_map(CUtensorMap* m, const void* ptr, long long rows, int K, int ck, int bn) {
+  EncodeTiledFn enc = get_encode();
+  SVK_REQUIRE(enc, SVK_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)ck, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = (ck == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SVK_REQUIRE(r == CUDA_SUCCESS, SVK_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+  return 0;
+}
+
+// Pick the bh x bw (<= max_rows pixels, bw <= max_bw) tile that wastes the fewest accumulator rows on an Hc x Wc grid.
+void pick_tile(int Hc, int Wc, int max_rows, int max_bw, int row_mult, int* bh_out, int* bw_out) {
+  double best = -1.0; int bbh = 1, bbw = 1;
+  for (int bw = 1; bw <= max_bw && bw <= max_rows; ++bw) {
+    int bh = max_rows / bw;
+    if (bh > Hc) bh = Hc;
+    if (bh > 128) bh = 128;
+    while (bh > 1 && (bh * bw) % row_mult != 0) --bh;
+    if ((bh * bw) % row_mult != 0) continue;
+    int th = (Hc + bh - 1) / bh, tw = (Wc + bw - 1) / bw;
+    double eff = (double)Hc * Wc / ((double)th * tw * max_rows);
+    if (row_mult > 1) eff = (double)Hc * Wc / ((double)th * tw * bh * bw);   // wgrad: cost ~ rows actually loaded
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > bbw)) { best = eff; bbh = bh; bbw = bw; }
+  }
+  *bh_out = bbh; *bw_out = bbw;
+}
+
+template <int KC, int BN>
+int launch_gather_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP& p, cudaStream_t st) {
+  typedef GatherCfg<KC, BN> Cfg;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_gather_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  int grid = p.total_tiles < svk_num_sms() ? p.total_tiles : svk_num_sms();
+  conv_tc_gather_kernel<KC, BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
+  SVK_LAUNCH_CHECK("conv_tc_gather");
+  return 0;
+}
+int launch_gather(int KC, int BN, const CUtensorMap& ta, const CUtensorMap& tb, const GatherP& p, cudaStream_t st) {
+#define SVK_G(K_, N_) if (KC == K_ && BN == N_) return launch_gather_t<K_, N_>(ta, tb, p, st)
+  SVK_G(64, 32); SVK_G(64, 64); SVK_G(64, 128); SVK_G(64, 256);
+  SVK_G(32, 32); SVK_G(32, 64); SVK_G(32, 128); SVK_G(32, 256);
+#undef SVK_G
+  svk_set_error("conv_tc: no kernel for KC=%d BN=%d", KC, BN);
+  return SVK_E_UNSUPPORTED;
+}
+
+// Common driver for fprop and the (per parity class) dgrad launches.
+int run_gather(const bf16* in, int N, int Hin, int Win, int Kc,           // gathered tensor
+               const bf16* w, int ntaps_total, int Nout,                  // packed weights [taps][Nout][Kc]
+               GatherP p, int es, cudaStream_t st) {
+  SVK_REQUIRE(Kc % 32 == 0 && Nout % 32 == 0 && Nout <= 512, SVK_E_UNSUPPORTED,
+              "conv_tc: channels must be multiples of 32 (<= 512 out), got Kc=%d Nout=%d", Kc, Nout);
+  const int KC = (Kc % 64 == 0) ? 64 : 32;
+  int BN = Nout;
+  if (BN > 256) BN = 256;
+  SVK_REQUIRE(BN == 32 || BN == 64 || BN == 128 || BN == 256, SVK_E_UNSUPPORTED, "conv_tc: Nout=%d unsupported", Nout);
+  SVK_REQUIRE(Nout % BN == 0, SVK_E_UNSUPPORTED, "conv_tc: Nout=%d not a multiple of %d", Nout, BN);
+  pick_tile(p.Hc, p.Wc, 128, 128 / (es > 1 ? 1 : 1), 1, &p.bh, &p.bw);
+  if (p.bw * es > 256) p.bw = 256 / es;
+  p.tiles_h = (p.Hc + p.bh - 1) / p.bh;
+  p.tiles_w = (p.Wc + p.bw - 1) / p.bw;
+  p.num_pix_tiles = N * p.tiles_h * p.tiles_w;
+  p.n_blocks = Nout / BN;
+  p.total_tiles = p.num_pix_tiles * p.n_blocks;
+  p.kchunks = Kc / KC;
+  p.Nout = Nout;
+  CUtensorMap ta, tb;
+  if (int e = make_nhwc_map(&ta, in, N, Hin, Win, Kc, KC, p.bw, p.bh, es)) return e;
+  if (int e = make_w_map(&tb, w, (long long)ntaps_total * Nout, Kc, KC, BN)) return e;
+  return launch_gather(KC, BN, ta, tb, p, st);
+}
+
+}  // namespace
+
+int svk_conv2d_fwd_tc(const svk_conv_desc* d, const void* x, const void* w, void* y, double* stats, const float* scale,
+                      const float* shift, const void* residual, int relu, const int* valid_wo, cudaStream_t st) {
+  GatherP p{};
+  p.Hc = d->Ho; p.Wc = d->Wo;
+  p.in_mul = d->stride;
+  p.ntaps = d->R * d->R;
+  const int pad = d->R / 2;
+  for (int r = 0; r < d->R; ++r)
+    for (int s = 0; s < d->R; ++s) { int t = r * d->R + s; p.tap_dh[t] = r - pad; p.tap_dw[t] = s - pad; p.tap_w[t] = t; }
+  p.Hout = d->Ho; p.Wout = d->Wo; p.o_mul = 1; p.o_off_h = 0; p.o_off_w = 0;
+  p.out = (bf16*)y; p.scale = scale; p.shift = shift; p.res = (const bf16*)residual; p.res_m = nullptr; p.mask = nullptr;
+  p.relu = relu; p.valid_w = valid_wo; p.stats = stats;
+  return run_gather((const bf16*)x, d->N, d->H, d->W, d->Cin, (const bf16*)w, d->R * d->R, d->Cout, p, d->stride, st);
+}
+
+int svk_conv2d_dgrad_tc(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
+                        const void* res_m, const void* mask, cudaStream_t st) {
+  const int pad = d->R / 2;
+  if (d->stride == 1) {
+    GatherP p{};
+    p.Hc = d->H; p.Wc = d->W; p.in_mul = 1; p.ntaps = d->R * d->R;
+    for (int r = 0; r < d->R; ++r)
+      for (int s = 0; s < d->R; ++s) { int t = r * d->R + s; p.tap_dh[t] = pad - r; p.tap_dw[t] = pad - s; p.tap_w[t] = t; }
+    p.Hout = d->H; p.Wout = d->W; p.o_mul = 1;
+    p.out = (bf16*)dx; p.res = (const bf16*)res; p.res_m = (const bf16*)res_m; p.mask = (const bf16*)mask;
+    return run_gather((const bf16*)dy, d->N, d->Ho, d->Wo, d->Cout, (const bf16*)w, d->R * d->R, d->Cin, p, 1, st);
+  }
+  // stride 2: one launch per output parity class (ph, pw); dx[2i+ph, 2j+pw] gathers dy[i+dh, j+dw] for the taps whose
+  // offset has the right parity.
+  if (d->R == 1) {
+    SVK_REQUIRE(res_m == nullptr, SVK_E_UNSUPPORTED, "conv2d_dgrad(tc, 1x1/s2): masked residual unsupported");
+    if (res != dx) {
+      SVK_REQUIRE(res == nullptr, SVK_E_UNSUPPORTED, "conv2d_dgrad(tc, 1x1/s2): res must be NULL or alias dx (accumulate)");
+      cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->N * d->H * d->W * d->Cin * 2, st);
+      SVK_REQUIRE(e == cudaSuccess, (int)e, "conv2d_dgrad: memset failed: %s", cudaGetErrorString(e));
+    }
+  }
+  for (int ph = 0; ph < 2; ++ph) {
+    for (int pw = 0; pw < 2; ++pw) {
+      GatherP p{};
+      p.Hc = (d->H - ph + 1) / 2; p.Wc = (d->W - pw + 1) / 2;
+      if (p.Hc <= 0 || p.Wc <= 0) continue;
+      p.in_mul = 1; p.ntaps = 0;
+      for (int r = 0; r < d->R; ++r) {
+        if (((ph + pad - r) & 1) != 0) continue;
+        for (int s = 0; s < d->R; ++s) {
+          if (((pw + pad - s) & 1) != 0) continue;
+          int t = p.ntaps++;
+          // floor division by 2 of (ph + pad - r) which is even (may be negative? ph+pad-r >= 0+1-2 = -1 -> only even values: 0 or 2... or -0)
+          p.tap_dh[t] = (ph + pad - r) / 2; p.tap_dw[t] = (pw + pad - s) / 2; p.tap_w[t] = r * d->R + s;
+        }
+      }
+      if (p.ntaps == 0) continue;   // 1x1/s2: only class (0,0) receives gradient
+      p.Hout = d->H; p.Wout = d->W; p.o_mul = 2; p.o_off_h = ph; p.o_off_w = pw;
+      p.out = (bf16*)dx; p.res = (const bf16*)res; p.res_m = (const bf16*)res_m; p.mask = (const bf16*)mask;
+      if (int e = run_gather((const bf16*)dy, d->N, d->Ho, d->Wo, d->Cout, (const bf16*)w, d->R * d->R, d->Cin, p, 1, st)) return e;
+    }
+  }
+  return 0;
+}
+
+int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  SVK_REQUIRE(d->Cin % 32 == 0 && d->Cout % 32 == 0, SVK_E_UNSUPPORTED, "conv2d_wgrad(tc): channels must be multiples of 32");
+  const int CK = (d->Cin % 64 == 0 && d->Cout % 64 == 0) ? 64 : 32;
+  WgradP p{};
+  p.stride = d->stride; p.R = d->R; p.Cin = d->Cin; p.Cout = d->Cout; p.ntaps = d->R * d->R; p.dw = dw;
+  p.cin_blk = d->Cin < 128 ? d->Cin : 128;
+  SVK_REQUIRE(d->Cin % p.cin_blk == 0, SVK_E_UNSUPPORTED, "conv2d_wgrad(tc): Cin=%d unsupported", d->Cin);
+  p.n_cin_blk = d->Cin / p.cin_blk;
+  p.n_m_blk = (d->Cout + 127) / 128;
+  int max_taps = 512 / p.cin_blk;
+  p.n_tap_grp = (p.ntaps + max_taps - 1) / max_taps;
+  p.taps_per_grp = (p.ntaps + p.n_tap_grp - 1) / p.n_tap_grp;
+  // pixel tile: P = bh*bw multiple of 16; smem = 2 A slots (128 ch) + 3 B slots (cin_blk ch), all P rows
+  int max_rows = 128;
+  int es = d->stride;
+  pick_tile(d->Ho, d->Wo, max_rows, 256 / es, 16, &p.bh, &p.bw);
+  p.P = p.bh * p.bw;
+  SVK_REQUIRE(p.P % 16 == 0 && p.P >= 16, SVK_E_UNSUPPORTED, "conv2d_wgrad(tc): no pixel tile for %dx%d", d->Ho, d->Wo);
+  p.tiles_h = (d->Ho + p.bh - 1) / p.bh;
+  p.tiles_w = (d->Wo + p.bw - 1) / p.bw;
+  p.num_pix_tiles = d->N * p.tiles_h * p.tiles_w;
+  int items = p.n_m_blk * p.n_cin_blk * p.n_tap_grp;
+  int ks = svk_num_sms() / items;
+  if (ks < 1) ks = 1;
+  if (ks > p.num_pix_tiles) ks = p.num_pix_tiles;
+  p.ksplit = ks;
+  CUtensorMap tdy, tx;
+  if (int e = make_nhwc_map(&tdy, dy, d->N, d->Ho, d->Wo, d->Cout, CK, p.bw, p.bh, 1)) return e;
+  if (int e = make_nhwc_map(&tx, x, d->N, d->H, d->W, d->Cin, CK, p.bw, p.bh, es)) return e;
+  size_t smem = (size_t)p.P * CK * 2 * ((128 / CK) * 2 + (p.cin_blk / CK) * WG_B_STAGES) + 1024 + 1024;
+  int grid = items * ks;
+  if (CK == 64) {
+    static bool cfg64 = false;
+    if (!cfg64) { cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); cfg64 = true; }
+    conv_tc_wgrad_kernel<64><<<grid, TC_THREADS, smem, st>>>(tdy, tx, p);
+  } else {
+    static bool cfg32 = false;
+    if (!cfg32) { cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); cfg32 = true; }
+    conv_tc_wgrad_kernel<32><<<grid, TC_THREADS, smem, st>>>(tdy, tx, p);
+  }
+  SVK_LAUNCH_CHECK("conv_tc_wgrad");
+  return 0;
+}
