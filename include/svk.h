@@ -83,7 +83,8 @@ int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* dy, floa
 
 /* Stem: 3x3 s1 p1 conv, Cin = 1, x is the (B,F,T) fp32 feature tensor itself.  replaces: model.py:247-249. */
 int svk_stem_conv_fwd(const float* x, const float* w /*[Cout][9]*/, void* y /*N,H,W,Cout*/, int N, int H, int W,
-                      int Cout, int dtype, const float* scale, const float* shift, int relu, void* stream);
+                      int Cout, int dtype, const float* scale, const float* shift, int relu,
+                      const int* valid_w /*nullable, per-utterance width: y[n,:,w>=valid_w[n],:] = 0*/, void* stream);
 int svk_stem_conv_wgrad(const float* x, const void* dy, float* dw /*[Cout][9], overwritten*/, int N, int H, int W,
                         int Cout, int dtype, void* stream);
 
@@ -151,11 +152,11 @@ int svk_aam_margin_bwd(float* dlogits, const long long* label, const float* cos_
 /* Cross entropy (mean over batch). loss_rows[b] = lse_b - logits[b,y_b]; lse[b] saved; rank[b] = number of
  * logits strictly greater than the target's (top-k correct iff rank < k).
  * replaces: nn.CrossEntropyLoss (train_resnet.py:201,317), accuracy.py:4-16. */
-int svk_ce_fwd(const float* logits, const long long* label, float* loss_rows, float* lse, int* rank, int B, int C,
-               void* stream);
-/* dlogits = (softmax - onehot) * gscale  (gscale = upstream_grad / B). gscale is a DEVICE scalar. */
-int svk_ce_bwd(const float* logits, const long long* label, const float* lse, const float* gscale, float* dlogits,
-               int B, int C, void* stream);
+int svk_ce_fwd(const float* logits, const long long* label, float* loss_rows, float* lse, int* rank,
+               float* loss_mean /*nullable; += loss_rows[b]/B, caller zeroes*/, int B, int C, void* stream);
+/* dlogits = (softmax - onehot) * (*gout) * mult   (gout = upstream gradient, a DEVICE scalar; mult = 1/B). */
+int svk_ce_bwd(const float* logits, const long long* label, const float* lse, const float* gout, float mult,
+               float* dlogits, int B, int C, void* stream);
 
 /* ---------------------------------------------------------------- optimiser ------------------------------ */
 /* torch.optim.SGD semantics on flat buffers: d = g*gscale + wd*p; buf = mom*buf + d; p -= lr*buf.

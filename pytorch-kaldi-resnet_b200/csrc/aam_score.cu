@@ -109,7 +109,8 @@ __device__ inline float block_reduce(float v, bool is_max, float* sm) {
 }
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ z, const long long* __restrict__ label,
                                                      float* __restrict__ loss_rows, float* __restrict__ lse,
-                                                     int* __restrict__ rank, int B, int C) {
+                                                     int* __restrict__ rank, float* __restrict__ loss_mean, int B,
+                                                     int C) {
   __shared__ float sm[32];
   int b = blockIdx.x;
   const float* p = z + (long long)b * C;
@@ -126,31 +127,32 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ z
     lse[b] = l;
     loss_rows[b] = l - zt;
     if (rank) rank[b] = (int)(cnt + 0.5f);
+    if (loss_mean) atomicAdd(loss_mean, (l - zt) / (float)B);
   }
 }
-SVK_API int svk_ce_fwd(const float* z, const long long* label, float* loss_rows, float* lse, int* rank, int B, int C,
-                       void* stream) {
+SVK_API int svk_ce_fwd(const float* z, const long long* label, float* loss_rows, float* lse, int* rank,
+                       float* loss_mean, int B, int C, void* stream) {
   SVK_REQUIRE(z && label && loss_rows && lse && B > 0 && C > 0, SVK_E_BADARG, "ce_fwd: bad args");
-  ce_fwd_kernel<<<B, 256, 0, as_stream(stream)>>>(z, label, loss_rows, lse, rank, B, C);
+  ce_fwd_kernel<<<B, 256, 0, as_stream(stream)>>>(z, label, loss_rows, lse, rank, loss_mean, B, C);
   SVK_LAUNCH_CHECK("ce_fwd");
   return 0;
 }
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ z, const long long* __restrict__ label,
-                                                     const float* __restrict__ lse, const float* __restrict__ gscale,
-                                                     float* __restrict__ g, int B, int C) {
+                                                     const float* __restrict__ lse, const float* __restrict__ gout,
+                                                     float mult, float* __restrict__ g, int B, int C) {
   long long n = (long long)B * C;
-  float gs = *gscale;
+  float gs = *gout * mult;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i / C), c = (int)(i % C);
     float p = expf(z[i] - lse[b]);
     g[i] = (p - ((long long)c == label[b] ? 1.f : 0.f)) * gs;
   }
 }
-SVK_API int svk_ce_bwd(const float* z, const long long* label, const float* lse, const float* gscale, float* g, int B,
-                       int C, void* stream) {
-  SVK_REQUIRE(z && label && lse && gscale && g && B > 0 && C > 0, SVK_E_BADARG, "ce_bwd: bad args");
+SVK_API int svk_ce_bwd(const float* z, const long long* label, const float* lse, const float* gout, float mult,
+                       float* g, int B, int C, void* stream) {
+  SVK_REQUIRE(z && label && lse && gout && g && B > 0 && C > 0, SVK_E_BADARG, "ce_bwd: bad args");
   long long n = (long long)B * C; long long b = (n + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
-  ce_bwd_kernel<<<(int)b, 256, 0, as_stream(stream)>>>(z, label, lse, gscale, g, B, C);
+  ce_bwd_kernel<<<(int)b, 256, 0, as_stream(stream)>>>(z, label, lse, gout, mult, g, B, C);
   SVK_LAUNCH_CHECK("ce_bwd");
   return 0;
 }

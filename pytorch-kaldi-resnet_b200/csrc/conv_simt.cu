@@ -320,7 +320,7 @@ template <typename T, int CO>
 __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        T* __restrict__ y, int N, int H, int W,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
-                                                       int relu) {
+                                                       int relu, const int* __restrict__ valid_w) {
   __shared__ float ws[CO * 9], ss[CO], sb[CO];
   for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) ws[i] = w[i];
   for (int i = threadIdx.x; i < CO; i += blockDim.x) { ss[i] = scale ? scale[i] : 1.f; sb[i] = shift ? shift[i] : 0.f; }
@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
   long long total = (long long)N * H * W;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
     int wq = (int)(p % W); long long q = p / W; int h = (int)(q % H);
+    const bool dead = valid_w && wq >= valid_w[(int)(q / H)];
     float v[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -347,14 +348,14 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc = fmaf(v[k], ws[(c0 + j) * 9 + k], acc);
         acc = fmaf(acc, ss[c0 + j], sb[c0 + j]);
-        o[j] = relu ? fmaxf(acc, 0.f) : acc;
+        o[j] = dead ? 0.f : (relu ? fmaxf(acc, 0.f) : acc);
       }
       Vec<T>::store(dst + c0, o);
     }
   }
 }
 SVK_API int svk_stem_conv_fwd(const float* x, const float* w, void* y, int N, int H, int W, int Cout, int dtype,
-                              const float* scale, const float* shift, int relu, void* stream) {
+                              const float* scale, const float* shift, int relu, const int* valid_w, void* stream) {
   SVK_REQUIRE(x && w && y && N > 0 && H > 0 && W > 0, SVK_E_BADARG, "stem_conv_fwd: bad args");
   SVK_REQUIRE(Cout == 32 || Cout == 64, SVK_E_UNSUPPORTED, "stem_conv_fwd: Cout must be 32 or 64, got %d", Cout);
   SVK_REQUIRE((scale == nullptr) == (shift == nullptr), SVK_E_BADARG, "stem_conv_fwd: scale and shift go together");
@@ -362,8 +363,8 @@ SVK_API int svk_stem_conv_fwd(const float* x, const float* w, void* y, int N, in
   long long b = (total + 127) / 128; long long cap = (long long)svk_num_sms() * 16; if (b > cap) b = cap;
   cudaStream_t st = as_stream(stream);
   SVK_DISPATCH_DTYPE(dtype, "stem_conv_fwd",
-    if (Cout == 32) stem_fwd_kernel<T, 32><<<(int)b, 128, 0, st>>>(x, w, (T*)y, N, H, W, scale, shift, relu);
-    else stem_fwd_kernel<T, 64><<<(int)b, 128, 0, st>>>(x, w, (T*)y, N, H, W, scale, shift, relu);)
+    if (Cout == 32) stem_fwd_kernel<T, 32><<<(int)b, 128, 0, st>>>(x, w, (T*)y, N, H, W, scale, shift, relu, valid_w);
+    else stem_fwd_kernel<T, 64><<<(int)b, 128, 0, st>>>(x, w, (T*)y, N, H, W, scale, shift, relu, valid_w);)
   SVK_LAUNCH_CHECK("stem_conv_fwd");
   return 0;
 }

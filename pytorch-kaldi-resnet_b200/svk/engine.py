@@ -1,0 +1,673 @@
+"""Host-side plan executor for the speaker-embedding network.
+
+`SpeakerNetEngine` owns (a) the flat fp32 parameter / gradient buffers the module's nn.Parameters are views of,
+(b) the packed conv weights, (c) per-shape activation workspaces, and strings the libsvk kernels into the
+forward / backward passes of the reference network:
+
+    reference                                   here
+    ---------                                   ----
+    ResNet.forward          model.py:246-269    _trunk_train / _trunk_eval
+    BasicBlock.forward      model.py:48-64      _block_fwd_train / _block_bwd / eval loop in _trunk_eval
+    StatsPooling.forward    model.py:441-455    svk_statspool_fwd/bwd
+    fc1                     model.py:384        svk_sgemm (+bias)
+    AAMLayer.forward        model.py:483-501    svk_l2norm_rows_* + svk_sgemm + svk_aam_margin_*
+    loss.backward()         train_resnet.py:327 _backward_train (one autograd.Function around the whole network)
+
+Activations are NHWC, bf16 (product) or fp32 (validation mode); torch is used for memory, streams and autograd
+plumbing only — every arithmetic step is a libsvk kernel.
+"""
+import math
+
+import torch
+
+from . import lib
+from .lib import call, make_conv_desc
+
+_EPS = 1e-5
+_MOM = 0.1
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _ConvRec(object):
+    """One conv layer: parameter holder + packed-weight views + geometry."""
+    __slots__ = ("mod", "cin", "cout", "R", "stride", "w_fwd", "w_dgrad", "dw_packed", "name")
+
+    def __init__(self, mod, name):
+        self.mod = mod
+        self.name = name
+        self.cout, self.cin, self.R, _ = mod.weight.shape
+        self.stride = mod.stride[0]
+        self.w_fwd = self.w_dgrad = self.dw_packed = None
+
+
+class _BNRec(object):
+    __slots__ = ("mod", "C", "idx", "name")
+
+    def __init__(self, mod, idx, name):
+        self.mod = mod
+        self.C = mod.weight.numel()
+        self.idx = idx
+        self.name = name
+
+
+class _BlockRec(object):
+    __slots__ = ("conv1", "bn1", "conv2", "bn2", "convd", "bnd", "name")
+
+
+class SpeakerNetEngine(object):
+    def __init__(self, model, precision="bf16", impl=None):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.model = model
+        self.precision = precision
+        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.dcode = lib.BF16 if precision == "bf16" else lib.F32
+        if impl is None:
+            impl = "tcgen05" if precision == "bf16" else "simt"
+        if impl not in ("tcgen05", "simt"):
+            raise ValueError("impl must be 'tcgen05' or 'simt'")
+        if impl == "tcgen05" and precision != "bf16":
+            raise ValueError("the tcgen05 convolution path is bf16 only")
+        self.impl = lib.IMPL_TCGEN05 if impl == "tcgen05" else lib.IMPL_SIMT
+        self.device = None
+        self._ws = {}
+        self._flat = None
+        self._eval_ready = False
+        self._packed_version = -1
+        self._param_version = 0
+        self._saved = None
+        self.grad_ready_cb = None       # called as cb(bucket_index) during backward (data-parallel hook)
+        self.debug = None               # tests set this to a dict to capture per-layer gradients (clones)
+        self._index_modules()
+
+    # ------------------------------------------------------------------------------------------ structure
+    def _index_modules(self):
+        m = self.model
+        res = m.res
+        self.convs, self.bns, self.blocks = [], [], []
+        self.stem_conv = res.conv1
+        self.stem_bn = self._bn(res.bn1, "res.bn1")
+        for li in range(1, 5):
+            layer = getattr(res, "layer%d" % li)
+            for bi, blk in enumerate(layer):
+                b = _BlockRec()
+                b.name = "res.layer%d.%d" % (li, bi)
+                b.conv1 = self._conv(blk.conv1, b.name + ".conv1")
+                b.bn1 = self._bn(blk.bn1, b.name + ".bn1")
+                b.conv2 = self._conv(blk.conv2, b.name + ".conv2")
+                b.bn2 = self._bn(blk.bn2, b.name + ".bn2")
+                if blk.downsample is not None:
+                    b.convd = self._conv(blk.downsample[0], b.name + ".downsample.0")
+                    b.bnd = self._bn(blk.downsample[1], b.name + ".downsample.1")
+                else:
+                    b.convd = b.bnd = None
+                self.blocks.append(b)
+        self.head_bn = self._bn(m.bn1, "bn1") if hasattr(m, "bn1") else None
+        self.c0 = self.stem_conv.weight.shape[0]
+        self.c_last = self.blocks[-1].conv2.cout
+        # gradient buckets (reverse execution order): 0 = head + fc1, 1 = layer4, 2 = everything before
+        self.bucket_of_block = [1 if b.name.startswith("res.layer4") else 2 for b in self.blocks]
+
+    def _conv(self, mod, name):
+        r = _ConvRec(mod, name)
+        self.convs.append(r)
+        return r
+
+    def _bn(self, mod, name):
+        r = _BNRec(mod, len(self.bns), name)
+        self.bns.append(r)
+        return r
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def params_in_order(self):
+        return [p for p in self.model.parameters()]
+
+    def ensure_device(self):
+        """Flatten parameters into one fp32 buffer (and gradients into another) on the module's CUDA device."""
+        params = self.params_in_order()
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise lib.SvkError("NeuralSpeakerModel runs on CUDA only (no CPU fallback): call .cuda() first")
+        if self._flat is not None and self._flat_ok(params):
+            return
+        lib.load()
+        self.device = dev
+        with torch.no_grad():
+            offs, total = [], 0
+            for p in params:
+                if p.dtype != torch.float32:
+                    raise lib.SvkError("parameters must be fp32 master weights")
+                offs.append(total)
+                total += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+            flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            grad = torch.zeros(total, dtype=torch.float32, device=dev)
+            for p, o in zip(params, offs):
+                v = flat[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                p._svk_flat = (self, o)
+                p.grad = None
+            self._flat, self._grad, self._offs, self._total = flat, grad, offs, total
+            self._grad_views = [grad[o:o + p.numel()].view(p.shape) for p, o in zip(params, offs)]
+            self._params = params
+            self._gview = {id(p): g for p, g in zip(params, self._grad_views)}
+            # bucket ranges in the flat buffer: [stem..layer3], [layer4], [fc1, head]
+            names = [n for n, _ in self.model.named_parameters()]
+            first_l4 = next(i for i, n in enumerate(names) if n.startswith("res.layer4"))
+            first_tail = next(i for i, n in enumerate(names) if not n.startswith("res."))
+            self.bucket_ranges = {2: (0, offs[first_l4]), 1: (offs[first_l4], offs[first_tail]),
+                                  0: (offs[first_tail], total)}
+            # packed conv weights + packed conv weight-gradient scratch
+            nconv = sum(c.cout * c.cin * c.R * c.R for c in self.convs)
+            self._wf = torch.empty(nconv, dtype=self.act_dtype, device=dev)
+            self._wd = torch.empty(nconv, dtype=self.act_dtype, device=dev)
+            self._dwp = torch.zeros(nconv, dtype=torch.float32, device=dev)
+            o = 0
+            for c in self.convs:
+                n = c.cout * c.cin * c.R * c.R
+                c.w_fwd, c.w_dgrad, c.dw_packed = self._wf[o:o + n], self._wd[o:o + n], self._dwp[o:o + n]
+                o += n
+            nb = len(self.bns)
+            self._nbt = torch.zeros(nb, dtype=torch.long, device=dev)
+            for bn in self.bns:
+                self._nbt[bn.idx] = bn.mod.num_batches_tracked.to(dev)
+                bn.mod._buffers["num_batches_tracked"] = self._nbt[bn.idx]
+            self._cmax = max(b.C for b in self.bns)
+            self._coef = torch.zeros(nb, 4, self._cmax, dtype=torch.float32, device=dev)  # scale, shift, mean, rstd
+            self._stats = torch.zeros(nb, 2 * self._cmax, dtype=torch.float64, device=dev)
+            self._bsums = torch.zeros(nb, 3 * self._cmax, dtype=torch.float64, device=dev)
+        self._ws = {}
+        self._eval_ready = False
+        self._packed_version = -1
+
+    def _flat_ok(self, params):
+        p0, p1 = params[0], params[-1]
+        return (getattr(p0, "_svk_flat", (None,))[0] is self and p0.data_ptr() == self._flat.data_ptr() and
+                p1.data_ptr() == self._flat.data_ptr() + 4 * self._offs[-1] and len(params) == len(self._offs))
+
+    def invalidate(self):
+        """Parameters or buffers changed behind our back (load_state_dict, optimizer step, .train())."""
+        self._param_version += 1
+        self._eval_ready = False
+
+    @property
+    def flat_params(self):
+        return self._flat
+
+    @property
+    def flat_grads(self):
+        return self._grad
+
+    def _pack_weights(self):
+        if self._packed_version == self._param_version:
+            return
+        st = _stream()
+        for c in self.convs:
+            call.svk_pack_conv_weight(c.mod.weight.data_ptr(), c.w_fwd.data_ptr(), c.w_dgrad.data_ptr(), c.cout, c.cin,
+                                      c.R, self.dcode, st)
+        self._packed_version = self._param_version
+
+    # ------------------------------------------------------------------------------------------ workspaces
+    def _workspace(self, key):
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) > 8:       # variable-length extraction: do not hoard one arena per length
+                self._ws.clear()
+            ws = {}
+            self._ws[key] = ws
+        return ws
+
+    def _buf(self, ws, name, shape, dtype=None):
+        t = ws.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype or self.act_dtype, device=self.device)
+            ws[name] = t
+        return t
+
+    def _arena(self, name, shape, dtype=None):
+        """Shape-agnostic scratch (variable-length extraction): a flat buffer per name, grown geometrically."""
+        dtype = dtype or self.act_dtype
+        n = 1
+        for s in shape:
+            n *= s
+        t = self._arena_bufs.get(name) if hasattr(self, "_arena_bufs") else None
+        if t is None or t.numel() < n or t.dtype != dtype or t.device != self.device:
+            if not hasattr(self, "_arena_bufs"):
+                self._arena_bufs = {}
+            t = torch.empty(int(n * 1.25) + 64, dtype=dtype, device=self.device)
+            self._arena_bufs[name] = t
+        return t[:n].view(shape)
+
+    def _coefs(self, bn):
+        c = self._coef[bn.idx]
+        return c[0], c[1], c[2], c[3]
+
+    # ------------------------------------------------------------------------------------------ kernels, thin wrappers
+    def _desc(self, N, H, W, conv):
+        return make_conv_desc(N, H, W, conv.cin, conv.cout, conv.R, conv.stride, self.dcode, self.impl)
+
+    def _conv_fwd(self, d, conv, x, y, stats=None, scale=None, shift=None, res=None, relu=0, valid=None):
+        call.svk_conv2d_fwd(d, x.data_ptr(), conv.w_fwd.data_ptr(), y.data_ptr(), _ptr(stats), _ptr(scale), _ptr(shift),
+                            _ptr(res), relu, _ptr(valid), _stream())
+
+    def _bn_train(self, bn, c, M, stats_done=False):
+        """Batch statistics of c ([M, C]) -> scale/shift (+ running-stat update)."""
+        st = _stream()
+        stats = self._stats[bn.idx]
+        if not stats_done:
+            call.svk_channel_stats(c.data_ptr(), M, bn.C, c_dtype_code(c), stats.data_ptr(), st)
+        sc, sh, mu, rs = self._coefs(bn)
+        m = bn.mod
+        call.svk_bn_finalize(stats.data_ptr(), M, bn.C, m.weight.data_ptr(), m.bias.data_ptr(),
+                             m.running_mean.data_ptr(), m.running_var.data_ptr(), _MOM, _EPS, sc.data_ptr(),
+                             sh.data_ptr(), mu.data_ptr(), rs.data_ptr(), st)
+        return sc, sh
+
+    def _bn_act(self, x, sc, sh, out, M, C, relu, res=None, rsc=None, rsh=None):
+        call.svk_bn_act_fwd(x.data_ptr(), sc.data_ptr(), sh.data_ptr(), _ptr(res), _ptr(rsc), _ptr(rsh), relu,
+                            out.data_ptr(), M, C, c_dtype_code(x), _stream())
+
+    # ------------------------------------------------------------------------------------------ training forward
+    def forward_train(self, x, y, with_head=True):
+        """x: (B, F, T) fp32 CUDA, y: (B,) int64 -> logits (B, spk_num) fp32.  Saves activations for backward."""
+        self.ensure_device()
+        self._param_version += 1        # parameters change every optimiser step: always re-pack, never reuse eval caches
+        self._eval_ready = False
+        self._pack_weights()
+        model = self.model
+        B, F, T = x.shape
+        x = x.contiguous().float()
+        ws = self._workspace(("train", B, F, T))
+        st = _stream()
+        self._stats.zero_()
+        self._nbt.add_(1)
+        sv = {"x": x, "B": B, "F": F, "T": T, "ws": ws, "blocks": []}
+        # ---- stem
+        C0 = self.c0
+        M = B * F * T
+        c0 = self._buf(ws, "c0", (B, F, T, C0))
+        a0 = self._buf(ws, "a0", (B, F, T, C0))
+        call.svk_stem_conv_fwd(x.data_ptr(), self.stem_conv.weight.data_ptr(), c0.data_ptr(), B, F, T, C0, self.dcode,
+                               0, 0, 0, 0, st)
+        sc, sh = self._bn_train(self.stem_bn, c0, M)
+        self._bn_act(c0, sc, sh, a0, M, C0, 1)
+        cur, H, W = a0, F, T
+        # ---- residual blocks
+        fused_stats = True          # svk_conv2d_fwd accumulates the BN statistics on both conv paths
+        for bi, b in enumerate(self.blocks):
+            d1 = self._desc(B, H, W, b.conv1)
+            Ho, Wo = d1.Ho, d1.Wo
+            Mo = B * Ho * Wo
+            Co = b.conv1.cout
+            c1 = self._buf(ws, "c1_%d" % bi, (B, Ho, Wo, Co))
+            a1 = self._buf(ws, "a1_%d" % bi, (B, Ho, Wo, Co))
+            c2 = self._buf(ws, "c2_%d" % bi, (B, Ho, Wo, Co))
+            out = self._buf(ws, "o_%d" % bi, (B, Ho, Wo, Co))
+            self._conv_fwd(d1, b.conv1, cur, c1, stats=self._stats[b.bn1.idx])
+            sc1, sh1 = self._bn_train(b.bn1, c1, Mo, stats_done=fused_stats)
+            self._bn_act(c1, sc1, sh1, a1, Mo, Co, 1)
+            d2 = self._desc(B, Ho, Wo, b.conv2)
+            self._conv_fwd(d2, b.conv2, a1, c2, stats=self._stats[b.bn2.idx])
+            sc2, sh2 = self._bn_train(b.bn2, c2, Mo, stats_done=fused_stats)
+            cd = dd = None
+            if b.convd is not None:
+                dd = self._desc(B, H, W, b.convd)
+                cd = self._buf(ws, "cd_%d" % bi, (B, Ho, Wo, Co))
+                self._conv_fwd(dd, b.convd, cur, cd, stats=self._stats[b.bnd.idx])
+                scd, shd = self._bn_train(b.bnd, cd, Mo, stats_done=fused_stats)
+                self._bn_act(c2, sc2, sh2, out, Mo, Co, 1, res=cd, rsc=scd, rsh=shd)
+            else:
+                self._bn_act(c2, sc2, sh2, out, Mo, Co, 1, res=cur)
+            sv["blocks"].append((cur, H, W, c1, a1, c2, cd, out, d1, d2, dd, Ho, Wo))
+            cur, H, W = out, Ho, Wo
+        # ---- pooling + embedding FC
+        mode = 1 if model.pool.pooling == "mean+std" else 0
+        Cl = self.c_last
+        pdim = Cl * H * (2 if mode else 1)
+        pooled = self._buf(ws, "pooled", (B, pdim), torch.float32)
+        call.svk_statspool_fwd(cur.data_ptr(), pooled.data_ptr(), B, H, W, Cl, mode, 0, self.dcode, st)
+        fc = model.fc1
+        E = fc.weight.shape[0]
+        emb = self._buf(ws, "emb", (B, E), torch.float32)
+        call.svk_sgemm(pooled.data_ptr(), pdim, 1, fc.weight.data_ptr(), 1, pdim, emb.data_ptr(), E, B, E, pdim, 1.0, 0.0,
+                       fc.bias.data_ptr(), st)
+        if not with_head:
+            return emb.clone()
+        sv.update(last=cur, Hl=H, Wl=W, mode=mode, pooled=pooled, emb=emb, pdim=pdim, E=E)
+        logits = self._head_fwd(emb, y, ws, sv, train=True)
+        self._saved = sv
+        return logits
+
+    # ------------------------------------------------------------------------------------------ heads
+    def _head_fwd(self, emb, y, ws, sv, train):
+        model = self.model
+        st = _stream()
+        B, E = emb.shape
+        loss = model.loss
+        h = emb
+        if loss in ("softmax", "AAM-v1"):
+            bn = self.head_bn
+            h = self._buf(ws, "head_h", (B, E), torch.float32)
+            if train:
+                sc, sh = self._bn_train(bn, emb, B)
+            else:
+                sc, sh = self._eval_coefs(bn)
+            call.svk_bn_act_fwd(emb.data_ptr(), sc.data_ptr(), sh.data_ptr(), 0, 0, 0, 1, h.data_ptr(), B, E, lib.F32, st)
+        last = model.last
+        C = last.weight.shape[0]
+        logits = torch.empty(B, C, dtype=torch.float32, device=self.device)
+        if loss == "softmax":
+            call.svk_sgemm(h.data_ptr(), E, 1, last.weight.data_ptr(), 1, E, logits.data_ptr(), C, B, C, E, 1.0, 0.0,
+                           last.bias.data_ptr(), st)
+        else:
+            if y is None:
+                raise lib.SvkError("AAM head needs labels: call model(x, y)")
+            y = y.contiguous()
+            xh = self._buf(ws, "aam_xh", (B, E), torch.float32)
+            xinv = self._buf(ws, "aam_xinv", (B,), torch.float32)
+            wh = self._buf(ws, "aam_wh", (C, E), torch.float32)
+            winv = self._buf(ws, "aam_winv", (C,), torch.float32)
+            cos_t = self._buf(ws, "aam_cos_t", (B,), torch.float32)
+            call.svk_l2norm_rows_fwd(h.data_ptr(), xh.data_ptr(), xinv.data_ptr(), B, E, 1e-12, st)
+            call.svk_l2norm_rows_fwd(last.weight.data_ptr(), wh.data_ptr(), winv.data_ptr(), C, E, 1e-12, st)
+            call.svk_sgemm(xh.data_ptr(), E, 1, wh.data_ptr(), 1, E, logits.data_ptr(), C, B, C, E, 1.0, 0.0, 0, st)
+            call.svk_aam_margin_fwd(logits.data_ptr(), y.data_ptr(), cos_t.data_ptr(), B, C, last.cos_m, last.sin_m,
+                                    last.th, last.mm, float(last.s), st)
+            if sv is not None:
+                sv.update(y=y, xh=xh, xinv=xinv, wh=wh, winv=winv, cos_t=cos_t)
+        if sv is not None:
+            sv.update(h=h, C=C)
+        return logits
+
+    def _head_bwd(self, dlogits, sv):
+        """dlogits (B, C) fp32 (consumed in place) -> d emb (B, E); writes head parameter gradients."""
+        model = self.model
+        st = _stream()
+        ws = sv["ws"]
+        B, E, C = sv["B"], sv["E"], sv["C"]
+        loss = model.loss
+        last = model.last
+        gw = self._gview[id(last.weight)]
+        h = sv["h"]
+        dh = self._buf(ws, "d_h", (B, E), torch.float32)
+        if loss == "softmax":
+            call.svk_sgemm(dlogits.data_ptr(), C, 1, last.weight.data_ptr(), E, 1, dh.data_ptr(), E, B, E, C, 1.0, 0.0, 0, st)
+            call.svk_sgemm(dlogits.data_ptr(), 1, C, h.data_ptr(), E, 1, gw.data_ptr(), E, C, E, B, 1.0, 0.0, 0, st)
+            call.svk_colsum(dlogits.data_ptr(), self._gview[id(last.bias)].data_ptr(), B, C, st)
+        else:
+            call.svk_aam_margin_bwd(dlogits.data_ptr(), sv["y"].data_ptr(), sv["cos_t"].data_ptr(), B, C, last.cos_m,
+                                    last.sin_m, last.th, float(last.s), st)
+            dxh = self._buf(ws, "d_xh", (B, E), torch.float32)
+            dwh = self._buf(ws, "d_wh", (C, E), torch.float32)
+            call.svk_sgemm(dlogits.data_ptr(), C, 1, sv["wh"].data_ptr(), E, 1, dxh.data_ptr(), E, B, E, C, 1.0, 0.0, 0, st)
+            call.svk_sgemm(dlogits.data_ptr(), 1, C, sv["xh"].data_ptr(), E, 1, dwh.data_ptr(), E, C, E, B, 1.0, 0.0, 0, st)
+            call.svk_l2norm_rows_bwd(dxh.data_ptr(), sv["xh"].data_ptr(), sv["xinv"].data_ptr(), dh.data_ptr(), B, E, st)
+            call.svk_l2norm_rows_bwd(dwh.data_ptr(), sv["wh"].data_ptr(), sv["winv"].data_ptr(), gw.data_ptr(), C, E, st)
+        if loss in ("softmax", "AAM-v1"):
+            bn = self.head_bn
+            sc, sh, mu, rs = self._coefs(bn)
+            sums = self._bsums[bn.idx]
+            demb = self._buf(ws, "d_emb", (B, E), torch.float32)
+            emb = sv["emb"]
+            call.svk_bn_bwd_reduce(dh.data_ptr(), h.data_ptr(), emb.data_ptr(), mu.data_ptr(), rs.data_ptr(), 0, 0, 0,
+                                   sums.data_ptr(), B, E, lib.F32, st)
+            call.svk_bn_bwd_apply(dh.data_ptr(), h.data_ptr(), emb.data_ptr(), mu.data_ptr(), rs.data_ptr(),
+                                  bn.mod.weight.data_ptr(), demb.data_ptr(), 0, 0, 0, 0, 0, sums.data_ptr(),
+                                  self._gview[id(bn.mod.weight)].data_ptr(), self._gview[id(bn.mod.bias)].data_ptr(),
+                                  0, 0, B, E, lib.F32, st)
+            return demb
+        return dh
+
+    # ------------------------------------------------------------------------------------------ training backward
+    def backward_train(self, dlogits):
+        sv = self._saved
+        if sv is None:
+            raise lib.SvkError("backward called without a saved forward")
+        self._saved = None
+        model = self.model
+        st = _stream()
+        ws = sv["ws"]
+        B = sv["B"]
+        self._bsums.zero_()
+        self._dwp.zero_()
+        dlogits = dlogits.contiguous().clone()      # the head backward works in place
+        demb = self._head_bwd(dlogits, sv)
+        # ---- fc1
+        fc = model.fc1
+        pdim, E = sv["pdim"], sv["E"]
+        pooled = sv["pooled"]
+        dpool = self._buf(ws, "d_pool", (B, pdim), torch.float32)
+        call.svk_sgemm(demb.data_ptr(), E, 1, fc.weight.data_ptr(), pdim, 1, dpool.data_ptr(), pdim, B, pdim, E, 1.0, 0.0, 0, st)
+        call.svk_sgemm(demb.data_ptr(), 1, E, pooled.data_ptr(), pdim, 1, self._gview[id(fc.weight)].data_ptr(), pdim,
+                       E, pdim, B, 1.0, 0.0, 0, st)
+        call.svk_colsum(demb.data_ptr(), self._gview[id(fc.bias)].data_ptr(), B, E, st)
+        self._bucket_done(0)
+        # ---- pooling
+        last, Hl, Wl, Cl = sv["last"], sv["Hl"], sv["Wl"], self.c_last
+        gmax = max(t[0].numel() for t in sv["blocks"])
+        gmax = max(gmax, max(t[7].numel() for t in sv["blocks"]))
+        gbuf = [self._buf(ws, "g%d" % i, (gmax,)) for i in range(5)]
+        dO = gbuf[0][:last.numel()].view(last.shape)
+        call.svk_statspool_bwd(last.data_ptr(), dpool.data_ptr(), dO.data_ptr(), B, Hl, Wl, Cl, sv["mode"], self.dcode, st)
+        cur_bucket = 1
+        # ---- blocks in reverse
+        for bi in range(len(self.blocks) - 1, -1, -1):
+            b = self.blocks[bi]
+            if self.bucket_of_block[bi] != cur_bucket:
+                self._bucket_done(cur_bucket)
+                cur_bucket = self.bucket_of_block[bi]
+            xin, H, W, c1, a1, c2, cd, out, d1, d2, dd, Ho, Wo = sv["blocks"][bi]
+            Mo = B * Ho * Wo
+            Co = b.conv1.cout
+            n_out = out.numel()
+            dc2 = gbuf[1][:n_out].view(out.shape)
+            da1 = gbuf[2][:n_out].view(out.shape)
+            dc1 = gbuf[3][:n_out].view(out.shape)
+            dcd = gbuf[4][:n_out].view(out.shape) if cd is not None else None
+            # free ping-pong slot for dx: dO lives in gbuf[0]; dx is written to gbuf[2] (da1 is dead by then)
+            _, _, mu2, rs2 = self._coefs(b.bn2)
+            sums2 = self._bsums[b.bn2.idx]
+            g2 = b.bn2.mod
+            if cd is not None:
+                _, _, mud, rsd = self._coefs(b.bnd)
+                gd = b.bnd.mod
+                call.svk_bn_bwd_reduce(dO.data_ptr(), out.data_ptr(), c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
+                                       cd.data_ptr(), mud.data_ptr(), rsd.data_ptr(), sums2.data_ptr(), Mo, Co, self.dcode, st)
+                call.svk_bn_bwd_apply(dO.data_ptr(), out.data_ptr(), c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
+                                      g2.weight.data_ptr(), dc2.data_ptr(), cd.data_ptr(), mud.data_ptr(), rsd.data_ptr(),
+                                      gd.weight.data_ptr(), dcd.data_ptr(), sums2.data_ptr(),
+                                      self._gview[id(g2.weight)].data_ptr(), self._gview[id(g2.bias)].data_ptr(),
+                                      self._gview[id(gd.weight)].data_ptr(), self._gview[id(gd.bias)].data_ptr(),
+                                      Mo, Co, self.dcode, st)
+            else:
+                call.svk_bn_bwd_reduce(dO.data_ptr(), out.data_ptr(), c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
+                                       0, 0, 0, sums2.data_ptr(), Mo, Co, self.dcode, st)
+                call.svk_bn_bwd_apply(dO.data_ptr(), out.data_ptr(), c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
+                                      g2.weight.data_ptr(), dc2.data_ptr(), 0, 0, 0, 0, 0, sums2.data_ptr(),
+                                      self._gview[id(g2.weight)].data_ptr(), self._gview[id(g2.bias)].data_ptr(), 0, 0,
+                                      Mo, Co, self.dcode, st)
+            # conv2: weight gradient + data gradient
+            if self.debug is not None:
+                self.debug[b.name] = dO.clone()
+                self.debug[b.name + ".conv2"] = dc2.clone()
+                if dcd is not None:
+                    self.debug[b.name + ".downsample.0"] = dcd.clone()
+            self._wgrad(d2, b.conv2, a1, dc2)
+            call.svk_conv2d_dgrad(d2, dc2.data_ptr(), b.conv2.w_dgrad.data_ptr(), da1.data_ptr(), 0, 0, 0, st)
+            # bn1 (+ReLU mask from a1)
+            _, _, mu1, rs1 = self._coefs(b.bn1)
+            sums1 = self._bsums[b.bn1.idx]
+            g1 = b.bn1.mod
+            call.svk_bn_bwd_reduce(da1.data_ptr(), a1.data_ptr(), c1.data_ptr(), mu1.data_ptr(), rs1.data_ptr(), 0, 0, 0,
+                                   sums1.data_ptr(), Mo, Co, self.dcode, st)
+            call.svk_bn_bwd_apply(da1.data_ptr(), a1.data_ptr(), c1.data_ptr(), mu1.data_ptr(), rs1.data_ptr(),
+                                  g1.weight.data_ptr(), dc1.data_ptr(), 0, 0, 0, 0, 0, sums1.data_ptr(),
+                                  self._gview[id(g1.weight)].data_ptr(), self._gview[id(g1.bias)].data_ptr(), 0, 0,
+                                  Mo, Co, self.dcode, st)
+            if self.debug is not None:
+                self.debug[b.name + ".conv1"] = dc1.clone()
+            self._wgrad(d1, b.conv1, xin, dc1)
+            dx = gbuf[2][:xin.numel()].view(xin.shape)
+            if cd is not None:
+                self._wgrad(dd, b.convd, xin, dcd)
+                call.svk_conv2d_dgrad(d1, dc1.data_ptr(), b.conv1.w_dgrad.data_ptr(), dx.data_ptr(), 0, 0, 0, st)
+                # 1x1/s2 data gradient accumulates into the block-input gradient (res aliases dx)
+                call.svk_conv2d_dgrad(dd, dcd.data_ptr(), b.convd.w_dgrad.data_ptr(), dx.data_ptr(), dx.data_ptr(), 0, 0, st)
+            else:
+                # identity shortcut: + dO * (out > 0), fused into the dgrad epilogue
+                call.svk_conv2d_dgrad(d1, dc1.data_ptr(), b.conv1.w_dgrad.data_ptr(), dx.data_ptr(), 0, dO.data_ptr(),
+                                      out.data_ptr(), st)
+            gbuf[0], gbuf[2] = gbuf[2], gbuf[0]
+            dO = dx
+        # ---- stem
+        if cur_bucket != 2:
+            self._bucket_done(cur_bucket)
+            cur_bucket = 2
+        F, T, C0 = sv["F"], sv["T"], self.c0
+        M = B * F * T
+        c0, a0 = ws["c0"], ws["a0"]
+        bn = self.stem_bn
+        _, _, mu, rs = self._coefs(bn)
+        sums = self._bsums[bn.idx]
+        dc0 = gbuf[1][:c0.numel()].view(c0.shape)
+        call.svk_bn_bwd_reduce(dO.data_ptr(), a0.data_ptr(), c0.data_ptr(), mu.data_ptr(), rs.data_ptr(), 0, 0, 0,
+                               sums.data_ptr(), M, C0, self.dcode, st)
+        call.svk_bn_bwd_apply(dO.data_ptr(), a0.data_ptr(), c0.data_ptr(), mu.data_ptr(), rs.data_ptr(),
+                              bn.mod.weight.data_ptr(), dc0.data_ptr(), 0, 0, 0, 0, 0, sums.data_ptr(),
+                              self._gview[id(bn.mod.weight)].data_ptr(), self._gview[id(bn.mod.bias)].data_ptr(), 0, 0,
+                              M, C0, self.dcode, st)
+        if self.debug is not None:
+            self.debug["res.conv1"] = dc0.clone()
+        call.svk_stem_conv_wgrad(sv["x"].data_ptr(), dc0.data_ptr(), self._gview[id(self.stem_conv.weight)].data_ptr(),
+                                 B, F, T, C0, self.dcode, st)
+        self._bucket_done(2)
+        # publish gradients: p.grad is a view of the flat gradient buffer (overwrite semantics)
+        for p, g in zip(self._params, self._grad_views):
+            if p.grad is not g:
+                p.grad = g
+
+    def _wgrad(self, d, conv, x, dy):
+        st = _stream()
+        call.svk_conv2d_wgrad(d, x.data_ptr(), dy.data_ptr(), conv.dw_packed.data_ptr(), st)
+        call.svk_unpack_conv_wgrad(conv.dw_packed.data_ptr(), self._gview[id(conv.mod.weight)].data_ptr(), conv.cout,
+                                   conv.cin, conv.R, st)
+
+    def _bucket_done(self, idx):
+        if self.grad_ready_cb is not None:
+            self.grad_ready_cb(idx)
+
+    # ------------------------------------------------------------------------------------------ eval / extraction
+    def _eval_coefs(self, bn):
+        sc, sh, _, _ = self._coefs_eval[bn.idx]
+        return sc, sh
+
+    def _prepare_eval(self):
+        if self._eval_ready:
+            return
+        self._pack_weights()
+        st = _stream()
+        if not hasattr(self, "_coef_eval_buf") or self._coef_eval_buf.device != self.device:
+            self._coef_eval_buf = torch.zeros(len(self.bns), 4, self._cmax, dtype=torch.float32, device=self.device)
+        self._coefs_eval = [self._coef_eval_buf[i] for i in range(len(self.bns))]
+        for bn in self.bns:
+            m = bn.mod
+            sc, sh = self._coefs_eval[bn.idx][0], self._coefs_eval[bn.idx][1]
+            call.svk_bn_eval_coeffs(m.weight.data_ptr(), m.bias.data_ptr(), m.running_mean.data_ptr(),
+                                    m.running_var.data_ptr(), _EPS, bn.C, sc.data_ptr(), sh.data_ptr(), st)
+        self._eval_ready = True
+
+    def forward_eval(self, x, y=None, lengths=None, with_head=False):
+        """Eval-mode network (BatchNorm folded into the conv epilogues).  x: (B, F, T) fp32, zero-padded past
+        `lengths` (int32 CUDA tensor of valid frame counts) when utterances of different length are batched; every
+        layer re-zeroes the padding so each row equals its batch-1 result (decode.py:198 semantics)."""
+        self.ensure_device()
+        self._prepare_eval()
+        model = self.model
+        B, F, T = x.shape
+        x = x.contiguous().float()
+        ws = self._workspace(("evalhead", B))
+        st = _stream()
+        valid = None
+        if lengths is not None:
+            valid = [lengths.to(torch.int32).contiguous()]
+            for _ in range(3):
+                valid.append(((valid[-1] + 1) // 2).to(torch.int32))
+        C0 = self.c0
+        a0 = self._arena("e_a0", (B, F, T, C0))
+        sc, sh = self._eval_coefs(self.stem_bn)
+        call.svk_stem_conv_fwd(x.data_ptr(), self.stem_conv.weight.data_ptr(), a0.data_ptr(), B, F, T, C0, self.dcode,
+                               sc.data_ptr(), sh.data_ptr(), 1, _ptr(valid[0]) if valid else 0, st)
+        cur, H, W = a0, F, T
+        stage = 0
+        for bi, b in enumerate(self.blocks):
+            d1 = self._desc(B, H, W, b.conv1)
+            Ho, Wo = d1.Ho, d1.Wo
+            Co = b.conv1.cout
+            if b.conv1.stride == 2:
+                stage += 1
+            v = valid[stage] if valid else None
+            a1 = self._arena("e_a1", (B, Ho, Wo, Co))
+            out = self._arena("e_o%d" % (bi % 2), (B, Ho, Wo, Co))
+            sc1, sh1 = self._eval_coefs(b.bn1)
+            self._conv_fwd(d1, b.conv1, cur, a1, scale=sc1, shift=sh1, relu=1, valid=v)
+            res = cur
+            if b.convd is not None:
+                dd = self._desc(B, H, W, b.convd)
+                cd = self._arena("e_cd", (B, Ho, Wo, Co))
+                scd, shd = self._eval_coefs(b.bnd)
+                self._conv_fwd(dd, b.convd, cur, cd, scale=scd, shift=shd, relu=0, valid=v)
+                res = cd
+            d2 = self._desc(B, Ho, Wo, b.conv2)
+            sc2, sh2 = self._eval_coefs(b.bn2)
+            self._conv_fwd(d2, b.conv2, a1, out, scale=sc2, shift=sh2, res=res, relu=1, valid=v)
+            cur, H, W = out, Ho, Wo
+        mode = 1 if model.pool.pooling == "mean+std" else 0
+        Cl = self.c_last
+        pdim = Cl * H * (2 if mode else 1)
+        pooled = self._arena("e_pool", (B, pdim), torch.float32)
+        call.svk_statspool_fwd(cur.data_ptr(), pooled.data_ptr(), B, H, W, Cl, mode, _ptr(valid[3]) if valid else 0,
+                               self.dcode, st)
+        fc = model.fc1
+        E = fc.weight.shape[0]
+        emb = torch.empty(B, E, dtype=torch.float32, device=self.device)
+        call.svk_sgemm(pooled.data_ptr(), pdim, 1, fc.weight.data_ptr(), 1, pdim, emb.data_ptr(), E, B, E, pdim, 1.0, 0.0,
+                       fc.bias.data_ptr(), st)
+        if not with_head:
+            return emb
+        return self._head_fwd(emb, y, ws, None, train=False)
+
+
+def c_dtype_code(t):
+    if t.dtype == torch.bfloat16:
+        return lib.BF16
+    if t.dtype == torch.float32:
+        return lib.F32
+    raise lib.SvkError("unsupported activation dtype %s" % t.dtype)
+
+
+class _NetFn(torch.autograd.Function):
+    """The whole network as ONE autograd node: forward = engine.forward_train, backward = engine.backward_train, which
+    writes parameter gradients straight into the flat gradient buffer (p.grad views) and returns no tensor grads."""
+
+    @staticmethod
+    def forward(ctx, engine, x, y, *params):
+        ctx.engine = engine
+        ctx.n = len(params)
+        return engine.forward_train(x, y)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ctx.engine.backward_train(dlogits)
+        return (None, None, None) + (None,) * ctx.n
+
+
+def run_train(engine, x, y):
+    engine.ensure_device()
+    return _NetFn.apply(engine, x, y, *engine._params)

@@ -1,0 +1,115 @@
+"""ctypes binding of libsvk.so (include/svk.h).  The product path fails loudly when the library is missing: there is
+no torch / CPU fallback anywhere in this package."""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvk.so")
+
+F32, BF16 = 0, 1
+IMPL_SIMT, IMPL_TCGEN05 = 0, 1
+
+
+class ConvDesc(Structure):
+    """Mirror of svk_conv_desc."""
+    _fields_ = [("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Ho", c_int), ("Wo", c_int),
+                ("Cout", c_int), ("R", c_int), ("stride", c_int), ("dtype", c_int), ("impl", c_int)]
+
+
+def make_conv_desc(N, H, W, Cin, Cout, R, stride, dtype, impl):
+    return ConvDesc(N, H, W, Cin, (H - 1) // stride + 1, (W - 1) // stride + 1, Cout, R, stride, dtype, impl)
+
+
+_P = c_void_p
+_I = c_int
+_L = c_longlong
+_F = c_float
+_D = POINTER(ConvDesc)
+
+# name -> argtypes, exactly as declared in include/svk.h (tests check every symbol is exported)
+SIGNATURES = {
+    "svk_pack_conv_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "svk_unpack_conv_wgrad": [_P, _P, _I, _I, _I, _P],
+    "svk_conv2d_fwd": [_D, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
+    "svk_conv2d_dgrad": [_D, _P, _P, _P, _P, _P, _P, _P],
+    "svk_conv2d_wgrad": [_D, _P, _P, _P, _P],
+    "svk_stem_conv_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P],
+    "svk_stem_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "svk_channel_stats": [_P, _L, _I, _I, _P, _P],
+    "svk_bn_finalize": [_P, _L, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P],
+    "svk_bn_eval_coeffs": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
+    "svk_bn_act_fwd": [_P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _I, _P],
+    "svk_bn_bwd_reduce": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "svk_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "svk_add_masked": [_P, _P, _P, _P, _L, _I, _P],
+    "svk_add_strided2": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "svk_statspool_fwd": [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
+    "svk_statspool_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "svk_sgemm": [_P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _F, _F, _P, _P],
+    "svk_colsum": [_P, _P, _I, _I, _P],
+    "svk_l2norm_rows_fwd": [_P, _P, _P, _I, _I, _F, _P],
+    "svk_l2norm_rows_bwd": [_P, _P, _P, _P, _I, _I, _P],
+    "svk_aam_margin_fwd": [_P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _P],
+    "svk_aam_margin_bwd": [_P, _P, _P, _I, _I, _F, _F, _F, _F, _P],
+    "svk_ce_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "svk_ce_bwd": [_P, _P, _P, _P, _F, _P, _I, _I, _P],
+    "svk_sgd_step": [_P, _P, _P, _L, _F, _F, _F, _F, _P],
+    "svk_cast": [_P, _P, _L, _I, _I, _P],
+    "svk_cosine_score_pairs": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
+    "svk_topk_meanstd": [_P, _I, _I, _I, _P, _P, _P],
+    "svk_snorm_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _P],
+}
+
+_lib = None
+
+
+class SvkError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libsvk.so once.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SvkError("libsvk.so not found at %s — build it with `python pytorch-kaldi-resnet_b200/csrc/build.py` "
+                       "(or __graft_entry__.build()); there is no fallback path" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.svk_version.restype = c_int
+    lib.svk_last_error_string.restype = c_char_p
+    lib.svk_launch_count.restype = c_longlong
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def launch_count():
+    return int(load().svk_launch_count())
+
+
+def check(rc, name):
+    if rc != 0:
+        msg = load().svk_last_error_string().decode("utf-8", "replace")
+        raise SvkError("%s failed (code %d): %s" % (name, rc, msg))
+
+
+class _Caller(object):
+    """`call.svk_xxx(args...)` -> runs the C function and raises SvkError on a non-zero return code."""
+
+    def __getattr__(self, name):
+        fn = getattr(load(), name)
+
+        def wrapped(*args):
+            rc = fn(*args)
+            if rc != 0:
+                check(rc, name)
+        setattr(self, name, wrapped)
+        return wrapped
+
+
+call = _Caller()

@@ -1,0 +1,81 @@
+"""Trial scoring on the GPU: cosine scoring of trial pairs, cohort top-k statistics for adaptive s-norm, s-norm apply.
+
+replaces the per-trial / per-utterance Python loops of the reference:
+    cosine_score.py:60-65            -> cosine_scores()          (svk_cosine_score_pairs)
+    compute_topk_mean_std.py:10-23   -> cohort_topk_meanstd()    (svk_l2norm_rows_fwd + svk_sgemm + svk_topk_meanstd)
+    adaptive_snorm.py:28-38          -> snorm_apply()            (svk_snorm_apply)
+Embeddings are float32 on the device, exactly what the reference feeds torch (`torch.FloatTensor(vec - mean)`).
+"""
+import torch
+
+from .lib import call
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, device):
+    return torch.as_tensor(t, dtype=torch.float32, device=device).contiguous()
+
+
+def _i32(t, device):
+    return torch.as_tensor(t, dtype=torch.int32, device=device).contiguous()
+
+
+def cosine_scores(enroll, test, mean, idx_enroll, idx_test, device="cuda"):
+    """score[t] = cosine(enroll[ie[t]] - mean, test[it[t]] - mean); mean may be None (already subtracted)."""
+    E, T = _f32(enroll, device), _f32(test, device)
+    ie, it = _i32(idx_enroll, device), _i32(idx_test, device)
+    m = None if mean is None else _f32(mean, device)
+    n, D = ie.numel(), E.shape[1]
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    if n == 0:
+        return out
+    call.svk_cosine_score_pairs(E.data_ptr(), T.data_ptr(), 0 if m is None else m.data_ptr(), ie.data_ptr(),
+                                it.data_ptr(), out.data_ptr(), n, D, _st())
+    return out
+
+
+def l2_normalize_rows(x, eps=1e-12):
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    call.svk_l2norm_rows_fwd(x.data_ptr(), out.data_ptr(), 0, x.shape[0], x.shape[1], eps, _st())
+    return out
+
+
+def cohort_topk_meanstd(vecs, cohort, topk=300, block_rows=4096, device="cuda"):
+    """For every row v of `vecs`: scores = normalize(cohort) @ normalize(v); top-k; (mean, unbiased std).
+    Both inputs must already be mean-subtracted (compute_topk_mean_std.py:41-48).  Returns (mean, std) tensors."""
+    X, Cm = _f32(vecs, device), _f32(cohort, device)
+    n, D = X.shape
+    nc = Cm.shape[0]
+    if nc < topk:
+        raise ValueError("cohort of %d rows is smaller than topk=%d (torch.topk would fail too)" % (nc, topk))
+    mean = torch.empty(n, dtype=torch.float32, device=device)
+    std = torch.empty(n, dtype=torch.float32, device=device)
+    if n == 0:
+        return mean, std
+    Cn = l2_normalize_rows(Cm)
+    Xn = l2_normalize_rows(X)
+    block_rows = max(1, min(block_rows, n))
+    scores = torch.empty(block_rows, nc, dtype=torch.float32, device=device)
+    st = _st()
+    for lo in range(0, n, block_rows):
+        rows = min(block_rows, n - lo)
+        xb = Xn[lo:lo + rows]
+        call.svk_sgemm(xb.data_ptr(), D, 1, Cn.data_ptr(), 1, D, scores.data_ptr(), nc, rows, nc, D, 1.0, 0.0, 0, st)
+        call.svk_topk_meanstd(scores.data_ptr(), rows, nc, topk, mean[lo:].data_ptr(), std[lo:].data_ptr(), st)
+    return mean, std
+
+
+def snorm_apply(scores, idx_enroll, idx_test, mean_e, std_e, mean_t, std_t, device="cuda"):
+    s = _f32(scores, device)
+    ie, it = _i32(idx_enroll, device), _i32(idx_test, device)
+    me, se, mt, sd = _f32(mean_e, device), _f32(std_e, device), _f32(mean_t, device), _f32(std_t, device)
+    out = torch.empty_like(s)
+    if s.numel() == 0:
+        return out
+    call.svk_snorm_apply(s.data_ptr(), ie.data_ptr(), it.data_ptr(), me.data_ptr(), se.data_ptr(), mt.data_ptr(),
+                         sd.data_ptr(), out.data_ptr(), s.numel(), _st())
+    return out
