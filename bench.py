@@ -1,0 +1,289 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the speaker-embedding hot path (BASELINE.json: "ResNet-34 AAM train chunks/sec").
+
+    python bench.py --gpus N --steps K --warmup W              our arm (libsvk, bf16 tcgen05 path)
+    python bench.py --impl reference --gpus N --steps K ...    the reference's CPU path (oracle port), host cores
+
+A "step" = one full training step of NeuralSpeakerModel(5994 speakers, 40-dim fbank, mean+std pooling, AAM m=0.2 s=30)
+on a batch of 256 synthetic 200-frame chunks PER GPU (BASELINE.json config 3: forward, cross-entropy, backward,
+bucketed NCCL gradient all-reduce when N > 1, SGD momentum 0.9 wd 5e-4).  `value` = chunks/s of the whole job with the
+batch resident in HBM; `e2e` = the same step through the public API (scripts/model.py + svk.loss + svk.optim) with
+the batch copied from pinned host memory every step and the loss read back every step.  One JSON line on stdout.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pytorch-kaldi-resnet_b200")
+for p in (ROOT, PKG, os.path.join(PKG, "scripts")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SPK, FEAT, FRAMES, BATCH = 5994, 40, 200, 256
+TRAIN_FLOP_PER_CHUNK = 13588306944          # SURVEY.md §8d / BASELINE.md §4 (C = 5994)
+METRIC, UNIT = "resnet34_aam_train_chunks_per_sec", "chunks/s"
+WORKLOAD = "cfg3: ResNet-34 AAM train step, bf16, batch 256/GPU x 200 frames x 40 fbank, 5994 speakers"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json, sustained)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def conv_flops(tag):
+    """Algorithmic FLOPs of one conv launch from its profile tag 'HxW Cin->Cout kR sS NN' (2*MACs, zero padding
+    counted as in SURVEY.md §8d: output pixels x Cout x R*R*Cin)."""
+    hw, ch, k, s, n = tag.split()
+    H, W = map(int, hw.split("x"))
+    ci, co = map(int, ch.split("->"))
+    R, S, N = int(k[1:]), int(s[1:]), int(n[1:])
+    Ho, Wo = (H - 1) // S + 1, (W - 1) // S + 1
+    return 2.0 * N * Ho * Wo * co * ci * R * R
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            hi = [s for s in sm if s >= 0.5 * max(sm)] or sm     # samples under load
+            out = {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(steps, warmup, batch=32, quiet=True):
+    """The reference's own CPU path for this metric: loop body of train_resnet.py:307-328 (forward, CE, backward, SGD)
+    on the host cores via the oracle port (run_aam_cpu.sh's train_resnet_cpu.py is missing from the reference and
+    train_resnet.py needs CUDA).  Each step is a bounded sample of the workload: `batch` chunks."""
+    import torch
+    from oracle import ref_model as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.init_state(SPK, FEAT, "mean+std", "AAM", seed=1234)
+    names = O.param_names(sd)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, FEAT, FRAMES, generator=g)
+    y = torch.randint(0, SPK, (batch,), generator=g)
+    bufs = [None] * len(names)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step(sd, names, x, y, "mean+std", "AAM", 0.2, 30, bufs, 0.1, 0.9, 5e-4)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * statistics.median(times)
+    return {"value": batch / (ms / 1e3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d steps of %d chunks (median) after %d warm-up, same model/shape, fp32 oneDNN" % (steps, batch, warmup),
+            "ms_per_step": ms}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 2))
+    cb = cpu_reference(steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "reference CPU path (oracle port of train_resnet.py:307-328) on the "
+                       "host cores; each step is a bounded sample of 32 chunks"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from model import NeuralSpeakerModel
+    from svk import lib
+    from svk.loss import CrossEntropyLoss
+    from svk.optim import SGD
+    from svk.parallel import DistributedDataParallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(1234)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = NeuralSpeakerModel(spk_num=SPK, feat_dim=FEAT, pooling="mean+std", loss="AAM", m=0.2, s=30).cuda(local)
+    model = DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
+    crit = CrossEntropyLoss()
+    opt = SGD(model.parameters(), 0.1, momentum=0.9, weight_decay=5e-4)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(B, FEAT, FRAMES, generator=g).pin_memory()
+    y_host = torch.randint(0, SPK, (B,), generator=g).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    model.train()
+
+    def step(x, y):
+        out = model(x, y)
+        loss = crit(out, y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, y_dev)
+    # ---- device-resident throughput
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = lib.launch_count()
+    ms_total = timed(lambda: step(x_dev, y_dev), args.steps)
+    launches = lib.launch_count() - n0
+    # ---- end to end through the public API: pinned host batch -> device every step, loss read back every step
+    def e2e_step():
+        xb = x_host.to(dev, non_blocking=True)
+        yb = y_host.to(dev, non_blocking=True)
+        return float(step(xb, yb).item())
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+    e2e_value = world * B / (ms_e2e / args.steps / 1e3)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "dp%d" % world,
+                       "l2": "no flush needed: one step streams ~4 GB of activations per GPU (>> 126 MB L2)",
+                       "algorithmic_tflops_per_gpu": TRAIN_FLOP_PER_CHUNK * B / (ms_step / 1e3) / 1e12},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "clocks": clocks}
+
+    if rank == 0:
+        # ---- per-kernel device times of one step, measured live with CUDA events on the launching stream
+        lib.profile_begin()
+        step(x_dev, y_dev)
+        prof = lib.profile_end()
+        agg = {}
+        for name, tag, ms in prof:
+            key = name
+            if name in ("svk_conv2d_fwd", "svk_conv2d_dgrad"):
+                key = "conv_tc_gather(fprop+dgrad)"
+            a = agg.setdefault(key, [0.0, 0, 0.0])
+            a[0] += ms
+            a[1] += 1
+            if tag:
+                a[2] += conv_flops(tag)
+        total_prof = sum(a[0] for a in agg.values())
+        top = max(agg.items(), key=lambda kv: kv[1][0])
+        hbm, tf, src = peaks()
+        kname, (kms, kn, kflop) = top
+        line["kernel_breakdown_ms"] = {k: round(v[0], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+        if kflop > 0:
+            ach = kflop / (kms / 1e3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": tf, "unit": "TFLOP/s",
+                                "frac": ach / tf, "traffic": None, "peak_source": src, "launches": kn,
+                                "avg_launch_ms": kms / kn, "share_of_step": kms / total_prof}
+        else:
+            line["roofline"] = {"bound": "hbm", "kernel": kname, "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None,
+                                "traffic": None, "peak_source": src, "share_of_step": kms / total_prof}
+        # wgrad kernel as a second roofline entry (same tensor bound)
+        wg = agg.get("svk_conv2d_wgrad")
+        if wg:
+            line["roofline_wgrad"] = {"bound": "tensor", "achieved": wg[2] / (wg[0] / 1e3) / 1e12, "peak": tf, "unit": "TFLOP/s",
+                                      "frac": wg[2] / (wg[0] / 1e3) / 1e12 / tf, "share_of_step": wg[0] / total_prof}
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference(3, 1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="chunks per GPU per step (256 = BASELINE.json config 3)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

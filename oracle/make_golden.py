@@ -34,7 +34,8 @@ def sample(t):
     """Deterministic strided subsample + norm + mean of a tensor (what the fixtures keep of large tensors)."""
     v = t.detach().double().reshape(-1)
     n = v.numel()
-    idx = torch.linspace(0, n - 1, min(NS, n)).long()
+    k = min(NS, n)
+    idx = (torch.arange(k, dtype=torch.int64) * (n - 1)) // max(k - 1, 1)      # integer arithmetic: host independent
     return np.concatenate([[float(v.norm()), float(v.mean()), float(n)], v[idx].numpy()]).astype(np.float64)
 
 
@@ -42,17 +43,30 @@ def checksum(sd):
     return {k: np.array([float(v.double().abs().sum()), float(v.double().sum())]) for k, v in sd.items()}
 
 
-def model_case(name, seed, spk_num, feat_dim, pooling, loss, B, T, m=0.2, s=30):
+def model_case(name, seed, spk_num, feat_dim, pooling, loss, B, T, m=0.2, s=30, tries=48):
     from model import NeuralSpeakerModel          # the reference's own class
     torch.manual_seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):
         ref = NeuralSpeakerModel(spk_num=spk_num, feat_dim=feat_dim, pooling=pooling, loss=loss, m=m, s=s)
-    g = torch.Generator().manual_seed(1000 + seed)
-    x = torch.randn(B, feat_dim, T, generator=g)
-    y = torch.randint(0, spk_num, (B,), generator=g)
     sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    # Pick the input (out of `tries` seeded draws) whose smallest |ReLU pre-activation| is largest: two correct fp32
+    # implementations differ by ~1e-7 in those values, and a sign flip there changes the backward mask of that element
+    # (and, through the tiny-batch BatchNorm sums, perturbs the whole layer) — a property of the test, not of the code.
+    best = None
+    for t_ in range(tries):
+        g = torch.Generator().manual_seed(1000 + seed + 7919 * t_)
+        xt = torch.randn(B, feat_dim, T, generator=g)
+        yt = torch.randint(0, spk_num, (B,), generator=g)
+        taps_ = {}
+        with torch.no_grad():
+            O.model_forward(sd0, xt, yt, pooling, loss, m, s, True, {}, taps_)
+        margin = min(float(v.abs().min()) for k, v in taps_.items() if k.startswith("pre/"))
+        if best is None or margin > best[0]:
+            best = (margin, xt, yt, t_)
+    margin, x, y, t_best = best
+    print("  input draw %d of %d: min |ReLU pre-activation| = %.3e" % (t_best, tries, margin))
     fx = {"seed": seed, "spk_num": spk_num, "feat_dim": feat_dim, "B": B, "T": T, "m": m, "s": s,
-          "x": x.numpy(), "y": y.numpy()}
+          "x": x.numpy(), "y": y.numpy(), "relu_margin": np.array(margin)}
     for k, v in checksum(sd0).items():
         fx["w/" + k] = v
 
@@ -237,8 +251,8 @@ if __name__ == "__main__":
         sys.exit("the reference is not mounted at %s: fixtures can only be generated in the build container" % REF)
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    model_case("aam_f40", seed=1, spk_num=37, feat_dim=40, pooling="mean+std", loss="AAM", B=2, T=48)
-    model_case("softmax_f30", seed=2, spk_num=11, feat_dim=30, pooling="mean", loss="softmax", B=3, T=51)
-    model_case("aamv1_f40", seed=3, spk_num=19, feat_dim=40, pooling="mean+std", loss="AAM-v1", B=2, T=40)
+    model_case("aam_f40", seed=1, spk_num=37, feat_dim=40, pooling="mean+std", loss="AAM", B=4, T=48)
+    model_case("softmax_f30", seed=2, spk_num=11, feat_dim=30, pooling="mean", loss="softmax", B=5, T=51)
+    model_case("aamv1_f40", seed=3, spk_num=19, feat_dim=40, pooling="mean+std", loss="AAM-v1", B=6, T=40)
     kat_case()
     scoring_case()

@@ -1,0 +1,283 @@
+"""Drop-in for the reference's scripts/train_resnet.py (same flags :25-91, same process model — mp.spawn one process
+per GPU :128, NCCL rendezvous :148 — same checkpoint dictionary :283-289, same log lines :412-427), with the hot loop
+(:307-328) running on the libsvk kernels: NeuralSpeakerModel (model.py) -> svk.loss.CrossEntropyLoss ->
+loss.backward() (one engine backward with bucketed NCCL all-reduce overlapped) -> svk.optim.SGD (one kernel).
+
+Deliberate differences, none of which changes the printed numbers: metrics are accumulated on the device and read
+back only every --print-freq steps (the reference syncs with loss.item() every step, :321); BatchNorm buffers are
+not re-broadcast every iteration (rank 0's are the ones checkpointed).
+"""
+import argparse
+import os
+import random
+import shutil
+import sys
+import time
+import warnings
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.utils.data
+import torch.utils.data.distributed
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.dirname(_HERE)
+for _p in (_HERE, _PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+from datasets import SequenceDataset, SequenceDataset2  # noqa: E402
+from model import NeuralSpeakerModel  # noqa: E402
+from svk.loss import CrossEntropyLoss, target_rank  # noqa: E402
+from svk.optim import SGD  # noqa: E402
+from svk.parallel import DistributedDataParallel  # noqa: E402
+
+parser = argparse.ArgumentParser(description='B200-native ResNet speaker-embedding training')
+parser.add_argument('--train-list', type=str, help='training scp')
+parser.add_argument('--cv-list', type=str, help='cv scp')
+parser.add_argument('--utt2spkid', type=str, help='utt2spkid')
+parser.add_argument('--input-dim', type=int, required=True, help='input feature dimension')
+parser.add_argument('--spk-num', type=int, required=True, help='number of speakers')
+parser.add_argument('--pooling', type=str, default='mean', help='mean or mean+std')
+parser.add_argument('--loss-type', type=str, default='softmax', help='softmax, AAM or AAM-v1')
+parser.add_argument('--margin', type=float, default=0.2, help='margin for AAM')
+parser.add_argument('--scale', type=float, default=30, help='scale for AAM')
+parser.add_argument('--dataset', type=str, default='v1', help='v1 or v2')
+parser.add_argument('--min-chunk-size', default=200, type=int, help='minimum feature map length (ignored, as in the reference)')
+parser.add_argument('--max-chunk-size', default=400, type=int, help='chunk length in frames')
+parser.add_argument('--log-dir', type=str, required=True, help='logging directory')
+parser.add_argument('-a', '--arch', metavar='ARCH', default='resnet18', help='recorded in the checkpoint only')
+parser.add_argument('-j', '--workers', default=2, type=int, metavar='N', help='number of data loading workers')
+parser.add_argument('--epochs', default=10, type=int, metavar='N')
+parser.add_argument('--start-epoch', default=0, type=int, metavar='N')
+parser.add_argument('-b', '--batch-size', default=128, type=int, metavar='N',
+                    help='total batch size of all GPUs on the node')
+parser.add_argument('--lr', '--learning-rate', default=0.1, type=float, metavar='LR', dest='lr')
+parser.add_argument('--lr-final', '--final-learning-rate', default=0.0001, type=float, metavar='LR', dest='lr_final')
+parser.add_argument('--momentum', default=0.9, type=float, metavar='M')
+parser.add_argument('--wd', '--weight-decay', default=1e-4, type=float, metavar='W', dest='weight_decay')
+parser.add_argument('-p', '--print-freq', default=10, type=int, metavar='N')
+parser.add_argument('--resume', default='', type=str, metavar='PATH')
+parser.add_argument('-e', '--evaluate', dest='evaluate', action='store_true')
+parser.add_argument('--pretrained', dest='pretrained', type=str, help='use pre-trained model')
+parser.add_argument('--world-size', default=-1, type=int, help='number of nodes')
+parser.add_argument('--rank', default=-1, type=int, help='node rank')
+parser.add_argument('--dist-url', default='tcp://224.66.41.62:23456', type=str)
+parser.add_argument('--dist-backend', default='nccl', type=str)
+parser.add_argument('--seed', default=None, type=int)
+parser.add_argument('--gpu', default=None, type=int, help='GPU id to use.')
+parser.add_argument('--gpu-num', default=-1, type=int, help='GPU nums to use.')
+parser.add_argument('--multiprocessing-distributed', action='store_true')
+# beyond the reference: numerics mode of the kernels
+parser.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'], help='activation storage (fp32 = validation mode)')
+
+best_acc1 = 0
+
+
+def main():
+    args = parser.parse_args()
+    if args.seed is not None:
+        random.seed(args.seed)
+        torch.manual_seed(args.seed)
+        warnings.warn('You have chosen to seed training; data-loader crops are still drawn from numpy per worker.')
+    if args.gpu is not None:
+        warnings.warn('You have chosen a specific GPU. This will completely disable data parallelism.')
+    if args.dist_url == "env://" and args.world_size == -1:
+        args.world_size = int(os.environ["WORLD_SIZE"])
+    args.distributed = args.world_size > 1 or args.multiprocessing_distributed
+    ngpus_per_node = torch.cuda.device_count() if args.gpu_num == -1 else min(torch.cuda.device_count(), args.gpu_num)
+    if ngpus_per_node == 0:
+        raise RuntimeError("train_resnet.py needs at least one CUDA device (there is no CPU path)")
+    if args.multiprocessing_distributed:
+        args.world_size = ngpus_per_node * args.world_size
+        mp.spawn(main_worker, nprocs=ngpus_per_node, args=(ngpus_per_node, args))
+    else:
+        main_worker(args.gpu, ngpus_per_node, args)
+
+
+def main_worker(gpu, ngpus_per_node, args):
+    global best_acc1
+    args.gpu = gpu if gpu is not None else 0
+    print("Use GPU: {} for training".format(args.gpu))
+    torch.cuda.set_device(args.gpu)
+    if args.distributed:
+        if args.dist_url == "env://" and args.rank == -1:
+            args.rank = int(os.environ["RANK"])
+        if args.multiprocessing_distributed:
+            args.rank = args.rank * ngpus_per_node + gpu
+        dist.init_process_group(backend=args.dist_backend, init_method=args.dist_url, world_size=args.world_size,
+                                rank=args.rank)
+    print("=> creating model '{}'".format(args.arch))
+    model = NeuralSpeakerModel(spk_num=args.spk_num, feat_dim=args.input_dim, pooling=args.pooling,
+                               loss=args.loss_type, m=args.margin, s=args.scale, precision=args.precision)
+    print('===> Model total parameter: {}'.format(sum(p.numel() for p in model.parameters() if p.requires_grad)))
+    loc = 'cuda:{}'.format(args.gpu)
+    if args.pretrained:
+        if os.path.isfile(args.pretrained):
+            print("=> using pre-trained model '{}'".format(args.pretrained))
+            checkpoint = torch.load(args.pretrained, map_location=loc, weights_only=False)
+            model.loadParameters(checkpoint['state_dict'])
+        else:
+            print("=> no pre-trained model found at '{}'".format(args.pretrained))
+            return
+    model.cuda(args.gpu)
+    if args.distributed:
+        args.batch_size = int(args.batch_size / ngpus_per_node)
+        args.workers = int((args.workers + ngpus_per_node - 1) / ngpus_per_node)
+        model = DistributedDataParallel(model, device_ids=[args.gpu])
+    print("gpu: {}, batch size: {}, args.workers:{}, ngpus_per_node: {}".format(gpu, args.batch_size, args.workers,
+                                                                               ngpus_per_node))
+    criterion = CrossEntropyLoss().cuda(args.gpu)
+    optimizer = SGD(model.parameters(), args.lr, momentum=args.momentum, weight_decay=args.weight_decay)
+    scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, args.epochs, eta_min=args.lr_final, last_epoch=-1)
+
+    if args.resume:
+        if os.path.isfile(args.resume):
+            print("=> loading checkpoint '{}'".format(args.resume))
+            checkpoint = torch.load(args.resume, map_location=loc, weights_only=False)
+            args.start_epoch = checkpoint['epoch']
+            best_acc1 = checkpoint['best_acc1']
+            state = checkpoint['state_dict']
+            if args.distributed and not any(k.startswith('module.') for k in state):
+                state = {'module.' + k: v for k, v in state.items()}
+            if not args.distributed:
+                state = {k[len('module.'):] if k.startswith('module.') else k: v for k, v in state.items()}
+            model.load_state_dict(state)
+            optimizer.load_state_dict(checkpoint['optimizer'])
+            # the reference rebuilds the schedule with a hard-coded eta_min here (train_resnet.py:225)
+            scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, args.epochs, eta_min=0.0001,
+                                                                   last_epoch=args.start_epoch - 1)
+            print("=> loaded checkpoint '{}' (epoch {})".format(args.resume, checkpoint['epoch']))
+        else:
+            print("=> no checkpoint found at '{}'".format(args.resume))
+
+    if args.dataset == "v2":
+        train_dataset = SequenceDataset2(scp_file=args.train_list, utt2spkid_file=args.utt2spkid, chunk_size=args.max_chunk_size)
+    else:
+        train_dataset = SequenceDataset(scp_file=args.train_list, utt2spkid_file=args.utt2spkid, chunk_size=[args.max_chunk_size])
+    train_sampler = None
+    if args.distributed:
+        train_sampler = torch.utils.data.distributed.DistributedSampler(train_dataset, num_replicas=args.world_size,
+                                                                        rank=args.rank, shuffle=True)
+    train_loader = torch.utils.data.DataLoader(train_dataset, batch_size=args.batch_size, shuffle=(train_sampler is None),
+                                               num_workers=args.workers, pin_memory=True, sampler=train_sampler)
+    print("=> args.world_size: {}, args.rank: {}, args.batch_size: {}, train_loader samples: {}".format(
+        args.world_size, args.rank, args.batch_size, len(train_loader)))
+    if args.dataset == "v2":
+        val = SequenceDataset2(scp_file=args.cv_list, utt2spkid_file=args.utt2spkid, chunk_size=args.max_chunk_size)
+    else:
+        val = SequenceDataset(scp_file=args.cv_list, utt2spkid_file=args.utt2spkid, chunk_size=[args.max_chunk_size])
+    val_loader = torch.utils.data.DataLoader(val, batch_size=args.batch_size, shuffle=False, num_workers=args.workers,
+                                             pin_memory=True)
+    if args.evaluate:
+        validate(val_loader, model, criterion, args)
+        return
+    os.makedirs(args.log_dir, exist_ok=True)
+    for epoch in range(args.start_epoch, args.epochs):
+        if args.distributed:
+            train_sampler.set_epoch(epoch)
+        train(train_loader, model, criterion, optimizer, epoch, args)
+        acc1 = validate(val_loader, model, criterion, args)
+        scheduler.step()
+        is_best = acc1 > best_acc1
+        best_acc1 = max(acc1, best_acc1)
+        if not args.multiprocessing_distributed or (args.multiprocessing_distributed and args.rank % ngpus_per_node == 0):
+            save_checkpoint({
+                'epoch': epoch + 1,
+                'arch': args.arch,
+                'state_dict': {k: v.detach().clone() for k, v in model.state_dict().items()},
+                'best_acc1': best_acc1,
+                'optimizer': optimizer.state_dict(),
+            }, is_best, os.path.join(args.log_dir, 'checkpoint_epoch{}.pth.tar'.format(epoch)))
+
+
+class DeviceMeters(object):
+    """loss / top-1 / top-5 sums kept on the device; one host read per display."""
+
+    def __init__(self, device):
+        self.acc = torch.zeros(4, dtype=torch.float64, device=device)   # sum loss*n, sum top1 hits, sum top5 hits, n
+        self.last = None
+
+    def update(self, loss, rank, n):
+        hits1 = (rank < 1).sum()
+        hits5 = (rank < 5).sum()
+        cur = torch.stack([loss.detach().double() * n, hits1.double(), hits5.double(),
+                           torch.tensor(float(n), dtype=torch.float64, device=loss.device)])
+        self.acc += cur
+        self.last = cur
+
+    def read(self):
+        tot, cur = self.acc.tolist(), self.last.tolist()
+        n, cn = max(tot[3], 1.0), max(cur[3], 1.0)
+        return {"loss": (cur[0] / cn, tot[0] / n), "acc1": (100.0 * cur[1] / cn, 100.0 * tot[1] / n),
+                "acc5": (100.0 * cur[2] / cn, 100.0 * tot[2] / n)}
+
+
+def _display(prefix, i, total, batch_time, data_time, stats):
+    digits = len(str(total))
+    entries = [prefix + ('[{:' + str(digits) + 'd}/{}]').format(i, total)]
+    entries.append('Time {:6.3f} ({:6.3f})'.format(*batch_time))
+    if data_time is not None:
+        entries.append('Data {:6.3f} ({:6.3f})'.format(*data_time))
+    entries.append('Loss {:.4e} ({:.4e})'.format(*stats["loss"]))
+    entries.append('Acc@1 {:6.2f} ({:6.2f})'.format(*stats["acc1"]))
+    entries.append('Acc@5 {:6.2f} ({:6.2f})'.format(*stats["acc5"]))
+    print('\t'.join(entries))
+    sys.stdout.flush()
+
+
+def train(train_loader, model, criterion, optimizer, epoch, args):
+    model.train()
+    meters = DeviceMeters(torch.device('cuda', args.gpu))
+    bt_sum = dt_sum = 0.0
+    end = time.time()
+    for i, (audios, target) in enumerate(train_loader):
+        dt = time.time() - end
+        audios = audios.cuda(args.gpu, non_blocking=True)
+        target = target.cuda(args.gpu, non_blocking=True)
+        output = model(audios, target)
+        loss = criterion(output, target)
+        meters.update(loss, target_rank(output, target), audios.size(0))
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        bt = time.time() - end
+        end = time.time()
+        bt_sum += bt
+        dt_sum += dt
+        if i % args.print_freq == 0:
+            _display("Epoch: [{}]".format(epoch), i, len(train_loader), (bt, bt_sum / (i + 1)), (dt, dt_sum / (i + 1)),
+                     meters.read())
+
+
+def validate(val_loader, model, criterion, args):
+    model.eval()
+    meters = DeviceMeters(torch.device('cuda', args.gpu))
+    bt_sum = 0.0
+    with torch.no_grad():
+        end = time.time()
+        for i, (audios, target) in enumerate(val_loader):
+            audios = audios.cuda(args.gpu, non_blocking=True)
+            target = target.cuda(args.gpu, non_blocking=True)
+            output = model(audios, target)          # the margin is applied in validation too (train_resnet.py:359)
+            loss = criterion(output, target)
+            meters.update(loss, target_rank(output, target), audios.size(0))
+            bt = time.time() - end
+            end = time.time()
+            bt_sum += bt
+            if i % args.print_freq == 0:
+                _display('Test: ', i, len(val_loader), (bt, bt_sum / (i + 1)), None, meters.read())
+        stats = meters.read() if meters.last is not None else {"acc1": (0, 0), "acc5": (0, 0)}
+        print(' * Acc@1 {:.3f} Acc@5 {:.3f}'.format(stats["acc1"][1], stats["acc5"][1]))
+    return stats["acc1"][1]
+
+
+def save_checkpoint(state, is_best, filename='checkpoint.pth.tar'):
+    torch.save(state, filename)
+    if is_best:
+        shutil.copyfile(filename, os.path.join(os.path.dirname(filename), 'model_best.pth.tar'))
+
+
+if __name__ == '__main__':
+    main()

@@ -99,17 +99,49 @@ def check(rc, name):
 
 
 class _Caller(object):
-    """`call.svk_xxx(args...)` -> runs the C function and raises SvkError on a non-zero return code."""
+    """`call.svk_xxx(args...)` -> runs the C function and raises SvkError on a non-zero return code.
+    With PROFILE set to a list (bench.py), every call is bracketed by CUDA events on the current stream and
+    (name, tag, start_event, end_event) is appended — per-kernel device times measured live, no profiler attached."""
 
     def __getattr__(self, name):
         fn = getattr(load(), name)
 
         def wrapped(*args):
+            if PROFILE is None:
+                rc = fn(*args)
+                if rc != 0:
+                    check(rc, name)
+                return
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             rc = fn(*args)
+            e1.record()
+            tag = ""
+            if args and isinstance(args[0], ConvDesc):
+                d = args[0]
+                tag = "%dx%d %d->%d k%d s%d N%d" % (d.H, d.W, d.Cin, d.Cout, d.R, d.stride, d.N)
+            PROFILE.append((name, tag, e0, e1))
             if rc != 0:
                 check(rc, name)
         setattr(self, name, wrapped)
         return wrapped
 
 
+PROFILE = None
 call = _Caller()
+
+
+def profile_begin():
+    global PROFILE
+    PROFILE = []
+
+
+def profile_end():
+    """-> list of (name, tag, milliseconds); synchronises the device."""
+    global PROFILE
+    import torch
+    torch.cuda.synchronize()
+    out = [(n, t, e0.elapsed_time(e1)) for n, t, e0, e1 in PROFILE]
+    PROFILE = None
+    return out

@@ -153,5 +153,6 @@ def sample_of(t, ns=96):
     """Same subsample as oracle/make_golden.py::sample (norm, mean, numel, strided values)."""
     v = t.detach().double().reshape(-1).cpu()
     n = v.numel()
-    idx = torch.linspace(0, n - 1, min(ns, n)).long()
+    k = min(ns, n)
+    idx = (torch.arange(k, dtype=torch.int64) * (n - 1)) // max(k - 1, 1)
     return np.concatenate([[float(v.norm()), float(v.mean()), float(n)], v[idx].numpy()])
