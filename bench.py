@@ -244,6 +244,17 @@ def run_ours(args):
             a[1] += 1
             if tag:
                 a[2] += conv_flops(tag)
+        if args.profile_out:
+            bytag = {}
+            for name, tag, ms in prof:
+                a = bytag.setdefault((name, tag), [0.0, 0])
+                a[0] += ms
+                a[1] += 1
+            rows = [{"kernel": k[0], "shape": k[1], "ms": round(v[0], 4), "launches": v[1],
+                     "tflops": (round(conv_flops(k[1]) * v[1] / (v[0] / 1e3) / 1e12, 1) if k[1] else None)}
+                    for k, v in sorted(bytag.items(), key=lambda kv: -kv[1][0])]
+            with open(args.profile_out, "w") as f:
+                json.dump(rows, f, indent=1)
         total_prof = sum(a[0] for a in agg.values())
         top = max(agg.items(), key=lambda kv: kv[1][0])
         hbm, tf, src = peaks()
@@ -278,6 +289,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="chunks per GPU per step (256 = BASELINE.json config 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default="", help="write the per-(kernel, shape) CUDA-event times of one step here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

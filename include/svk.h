@@ -59,8 +59,6 @@ typedef struct svk_conv_desc {
  * [R*R][Cin][Cout] (w_dgrad), both in `dtype`.  Either output may be NULL. */
 int svk_pack_conv_weight(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int R,
                          int dtype, void* stream);
-/* packed fp32 [R*R][Cout][Cin] weight gradient -> OIHW fp32 (overwrites dw_oihw). */
-int svk_unpack_conv_wgrad(const float* dw_packed, float* dw_oihw, int Cout, int Cin, int R, void* stream);
 
 /* y = conv(x, w).  Epilogue (all optional, applied in this order on the fp32 accumulator):
  *   v = acc * scale[c] + shift[c]          (scale/shift both non-NULL: folded eval-mode BatchNorm)
@@ -77,9 +75,13 @@ int svk_conv2d_fwd(const svk_conv_desc* d, const void* x, const void* w_fwd, voi
  * (dy is N,Ho,Wo,Cout; dx is N,H,W,Cin).  replaces: cuDNN dgrad under loss.backward(), train_resnet.py:327. */
 int svk_conv2d_dgrad(const svk_conv_desc* d, const void* dy, const void* w_dgrad, void* dx, const void* res,
                      const void* res_m, const void* mask, void* stream);
-/* dw_packed[R*R][Cout][Cin] (fp32) += dy^T * im2col(x).  Caller zeroes dw_packed first (split-K uses atomics).
+/* dw_oihw[Cout][Cin][R][R] (fp32, overwritten) = dy^T * im2col(x).  Split-K over pixel tiles: every CTA writes its
+ * partial sum into `workspace` with plain stores, then one reduction kernel sums the partials in a fixed order and
+ * transposes to OIHW (deterministic, no atomics).  workspace_bytes >= svk_conv2d_wgrad_workspace_bytes(d).
  * replaces: cuDNN wgrad under loss.backward(), train_resnet.py:327. */
-int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream);
+size_t svk_conv2d_wgrad_workspace_bytes(const svk_conv_desc* d);
+int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* dy, float* dw_oihw, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* Stem: 3x3 s1 p1 conv, Cin = 1, x is the (B,F,T) fp32 feature tensor itself.  replaces: model.py:247-249. */
 int svk_stem_conv_fwd(const float* x, const float* w /*[Cout][9]*/, void* y /*N,H,W,Cout*/, int N, int H, int W,

@@ -135,12 +135,12 @@ __global__ void __launch_bounds__(NT) conv_gather_kernel(GatherArgs a) {
 }
 
 struct WgradArgs {
-  const void* x; const void* dy; float* dw;
+  const void* x; const void* dy; float* dw;   // dw: split-K partials [gridDim.z][taps][Cout][Cin]
   int N, H, W, Cin, Ho, Wo, Cout, R, stride;
   long long kslice;  // pixels per z-slice
 };
 
-// dw[tap][co][ci] += sum_pix dy[pix, co] * x[shift_tap(pix), ci]
+// partial[z][tap][co][ci] = sum over this z-slice's pixels of dy[pix, co] * x[shift_tap(pix), ci]
 template <typename T>
 __global__ void __launch_bounds__(NT) conv_wgrad_simt_kernel(WgradArgs a) {
   __shared__ float As[BK][BM + 4];
@@ -201,9 +201,9 @@ __global__ void __launch_bounds__(NT) conv_wgrad_simt_kernel(WgradArgs a) {
   for (int i = 0; i < 4; ++i) {
     int co = co0 + ty * 4 + i;
     if (co >= a.Cout) continue;
-    float* dst = a.dw + ((long long)otap * a.Cout + co) * a.Cin + oci;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(dst + j, acc[i][j]);
+    float* dst = a.dw + (long long)blockIdx.z * ((long long)a.R * a.R * a.Cout * a.Cin) +
+                 ((long long)otap * a.Cout + co) * a.Cin + oci;
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
 }
 
@@ -242,24 +242,42 @@ int svk_conv2d_dgrad_simt(const svk_conv_desc* d, const void* dy, const void* w,
   SVK_LAUNCH_CHECK("conv2d_dgrad(simt)");
   return 0;
 }
-int svk_conv2d_wgrad_simt(const svk_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
-  WgradArgs a{x, dy, dw, d->N, d->H, d->W, d->Cin, d->Ho, d->Wo, d->Cout, d->R, d->stride, 0};
+static void simt_wgrad_plan(const svk_conv_desc* d, long long* kslice, int* gz) {
   int gx = (d->Cout + BM - 1) / BM, gy = (d->R * d->R * d->Cin + BN - 1) / BN;
   long long K = (long long)d->N * d->Ho * d->Wo;
   long long want = (long long)svk_num_sms() * 4 / ((long long)gx * gy) + 1;   // ~4 CTAs per SM in total
   long long maxsl = (K + 255) / 256;                                          // at least 256 pixels per slice
   if (want > maxsl) want = maxsl;
   if (want < 1) want = 1;
-  if (want > 65535) want = 65535;
+  if (want > 1024) want = 1024;
   long long ks = (K + want - 1) / want;
   ks = (ks + BK - 1) / BK * BK;
-  a.kslice = ks;
-  int gz = (int)((K + ks - 1) / ks);
+  *kslice = ks;
+  *gz = (int)((K + ks - 1) / ks);
+}
+int svk_conv2d_wgrad_simt(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats,
+                          int* ksplit_out, cudaStream_t st) {
+  WgradArgs a{x, dy, ws, d->N, d->H, d->W, d->Cin, d->Ho, d->Wo, d->Cout, d->R, d->stride, 0};
+  int gx = (d->Cout + BM - 1) / BM, gy = (d->R * d->R * d->Cin + BN - 1) / BN, gz;
+  simt_wgrad_plan(d, &a.kslice, &gz);
+  SVK_REQUIRE((size_t)gz * d->R * d->R * d->Cout * d->Cin <= ws_floats, SVK_E_BADARG, "conv2d_wgrad(simt): workspace too small");
   dim3 grid(gx, gy, gz);
   if (d->dtype == SVK_F32) conv_wgrad_simt_kernel<float><<<grid, NT, 0, st>>>(a);
   else conv_wgrad_simt_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(a);
   SVK_LAUNCH_CHECK("conv2d_wgrad(simt)");
+  *ksplit_out = gz;
   return 0;
+}
+
+// dw_oihw[co][ci][tap] = sum_k partial[k][tap][co][ci]: split-K reduction fused with the packed -> OIHW transpose.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int ksplit, long long stride,
+                                                           float* __restrict__ dw, int Cout, int Cin, int taps) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < stride; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < ksplit; ++k) s += ws[(long long)k * stride + i];
+    int ci = (int)(i % Cin); long long r = i / Cin; int co = (int)(r % Cout); int t = (int)(r / Cout);
+    dw[((long long)co * Cin + ci) * taps + t] = s;
+  }
 }
 
 // implemented in conv_tc.cu
@@ -267,7 +285,9 @@ int svk_conv2d_fwd_tc(const svk_conv_desc* d, const void* x, const void* w, void
                       const float* shift, const void* residual, int relu, const int* valid_wo, cudaStream_t st);
 int svk_conv2d_dgrad_tc(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
                         const void* res_m, const void* mask, cudaStream_t st);
-int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st);
+int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats, int* ksplit_out,
+                        cudaStream_t st);
+size_t svk_conv2d_wgrad_tc_ws_floats(const svk_conv_desc* d);
 
 SVK_API int svk_conv2d_fwd(const svk_conv_desc* d, const void* x, const void* w, void* y, double* stats,
                            const float* scale, const float* shift, const void* residual, int relu,
@@ -302,16 +322,33 @@ SVK_API int svk_conv2d_dgrad(const svk_conv_desc* d, const void* dy, const void*
   return svk_conv2d_dgrad_simt(d, dy, w, dx, res, res_m, mask, st);
 }
 
-SVK_API int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
+SVK_API size_t svk_conv2d_wgrad_workspace_bytes(const svk_conv_desc* d) {
+  if (check_desc("conv2d_wgrad_workspace_bytes", d)) return 0;
+  if (d->impl == SVK_IMPL_TCGEN05) return svk_conv2d_wgrad_tc_ws_floats(d) * sizeof(float);
+  long long ks; int gz;
+  simt_wgrad_plan(d, &ks, &gz);
+  return (size_t)gz * d->R * d->R * d->Cout * d->Cin * sizeof(float);
+}
+
+SVK_API int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* dy, float* dw_oihw, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   if (int e = check_desc("conv2d_wgrad", d)) return e;
-  SVK_REQUIRE(x && dy && dw, SVK_E_BADARG, "conv2d_wgrad: null pointer");
+  SVK_REQUIRE(x && dy && dw_oihw && workspace, SVK_E_BADARG, "conv2d_wgrad: null pointer");
+  SVK_REQUIRE(aligned16(workspace), SVK_E_ALIGN, "conv2d_wgrad: workspace must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
+  int ksplit = 0;
   if (d->impl == SVK_IMPL_TCGEN05) {
     SVK_REQUIRE(d->dtype == SVK_BF16, SVK_E_UNSUPPORTED, "conv2d_wgrad: tcgen05 path is bf16 only");
-    return svk_conv2d_wgrad_tc(d, x, dy, dw, st);
+    if (int e = svk_conv2d_wgrad_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
+  } else {
+    SVK_REQUIRE(d->impl == SVK_IMPL_SIMT, SVK_E_BADARG, "conv2d_wgrad: bad impl %d", d->impl);
+    if (int e = svk_conv2d_wgrad_simt(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
   }
-  SVK_REQUIRE(d->impl == SVK_IMPL_SIMT, SVK_E_BADARG, "conv2d_wgrad: bad impl %d", d->impl);
-  return svk_conv2d_wgrad_simt(d, x, dy, dw, st);
+  long long stride = (long long)d->R * d->R * d->Cout * d->Cin;
+  long long b = (stride + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
+  wgrad_reduce_kernel<<<(int)b, 256, 0, st>>>((const float*)workspace, ksplit, stride, dw_oihw, d->Cout, d->Cin, d->R * d->R);
+  SVK_LAUNCH_CHECK("conv2d_wgrad(reduce)");
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ stem (Cin = 1)

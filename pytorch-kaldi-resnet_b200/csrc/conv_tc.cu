@@ -360,11 +360,15 @@ struct WgradP {
   int R;
   int Cin, Cout;
   int cin_blk, n_cin_blk, n_m_blk, n_tap_grp, taps_per_grp, ntaps;
-  int ksplit;                 // CTAs per (m_blk, cin_blk, tap group)
-  float* dw;                  // packed [taps][Cout][Cin] fp32
+  int ksplit;                 // CTAs per (m_blk, cin_blk, tap group); every one of them owns >= 1 pixel tile
+  int tiles_per;              // pixel tiles per CTA
+  int rshift;                 // 1: 3x3/s1 — a tap group is one filter COLUMN s; its three taps r=0..2 read the same
+                              //    (bh+2) x bw halo tile of x at K offsets r*bw rows (one TMA load instead of three)
+  int xrows;                  // rows of one x tile in smem: (bh+2)*bw (rshift) or P
+  int b_stages;               // x-tile ring depth (2 or 3)
+  float* ws;                  // split-K partials [ksplit][taps][Cout][Cin] fp32 (plain stores, no atomics)
+  long long ws_stride;        // taps*Cout*Cin
 };
-
-constexpr int WG_B_STAGES = 3;
 
 // CK = channels per swizzle atom row: 64 (SW128) when both Cin and Cout are multiples of 64, else 32 (SW64).
 template <int CK>
@@ -379,22 +383,23 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int m_chunks = 128 / CK;                       // dy atoms fetched per tile (only those < Cout are real)
+  const int m_chunks = 128 / CK;                       // dy atoms per tile slot (only those < Cout are fetched)
   const int a_real = (p.Cout < 128 ? p.Cout : 128) / CK;
   const int b_chunks = p.cin_blk / CK;
-  const uint32_t atom_bytes = (uint32_t)p.P * ROWB;    // one CK-channel chunk of a pixel tile
-  const uint32_t A_BYTES = atom_bytes * m_chunks;
-  const uint32_t B_BYTES = atom_bytes * b_chunks;
-  const uint32_t a0 = base;                            // 2 A slots
-  const uint32_t b0 = base + 2 * A_BYTES;              // WG_B_STAGES B slots
-  const uint32_t auxoff = 2 * A_BYTES + WG_B_STAGES * B_BYTES;
+  const uint32_t a_atom = (uint32_t)p.P * ROWB;        // one CK-channel chunk of a dy tile
+  const uint32_t b_atom = (uint32_t)p.xrows * ROWB;    // one CK-channel chunk of an x tile
+  const uint32_t A_BYTES = a_atom * m_chunks;
+  const uint32_t B_BYTES = b_atom * b_chunks;
+  const uint32_t a0 = base;                            // 2 dy slots
+  const uint32_t b0 = base + 2 * A_BYTES;              // b_stages x slots
+  const uint32_t auxoff = 2 * A_BYTES + p.b_stages * B_BYTES;
   const uint32_t aux = base + auxoff;
   const uint32_t bar_afull = aux, bar_aempty = aux + 16, bar_bfull = aux + 32, bar_bempty = aux + 64, bar_done = aux + 96;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + auxoff + 128);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
-    for (int s = 0; s < WG_B_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
     mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -413,11 +418,14 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   const int tg = wi % p.n_tap_grp; wi /= p.n_tap_grp;
   const int cb = wi % p.n_cin_blk;
   const int mb = wi / p.n_cin_blk;
-  const int tap0 = tg * p.taps_per_grp;
-  const int ntap = (p.ntaps - tap0) < p.taps_per_grp ? (p.ntaps - tap0) : p.taps_per_grp;
-  const int tiles_per = (p.num_pix_tiles + p.ksplit - 1) / p.ksplit;
-  const int t_beg = ks * tiles_per;
-  const int t_end = (t_beg + tiles_per) < p.num_pix_tiles ? (t_beg + tiles_per) : p.num_pix_tiles;
+  // taps of this group: rshift -> (r, s = tg) for r = 0..R-1;  else tap0 .. tap0+ntap-1
+  const int tap0 = p.rshift ? tg : tg * p.taps_per_grp;
+  const int tap_step = p.rshift ? p.R : 1;
+  const int ntap = p.rshift ? p.R : ((p.ntaps - tap0) < p.taps_per_grp ? (p.ntaps - tap0) : p.taps_per_grp);
+  const int loads = p.rshift ? 1 : ntap;               // x-tile loads per pixel tile
+  const int taps_per_load = p.rshift ? ntap : 1;
+  const int t_beg = ks * p.tiles_per;
+  const int t_end = (t_beg + p.tiles_per) < p.num_pix_tiles ? (t_beg + p.tiles_per) : p.num_pix_tiles;
   const int pad = p.R / 2;
 
   if (warp == 0) {
@@ -431,19 +439,19 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
         const int n = pt / p.tiles_h;
         const int h0 = th * p.bh, w0 = tw * p.bw;
         mbar_wait(bar_aempty + 8 * as, aph ^ 1u);
-        mbar_expect_tx(bar_afull + 8 * as, atom_bytes * a_real);
+        mbar_expect_tx(bar_afull + 8 * as, a_atom * a_real);
         for (int c = 0; c < a_real; ++c)
-          tma_load_4d(a0 + as * A_BYTES + c * atom_bytes, &tmDy, bar_afull + 8 * as, mb * 128 + c * CK, w0, h0, n);
+          tma_load_4d(a0 + as * A_BYTES + c * a_atom, &tmDy, bar_afull + 8 * as, mb * 128 + c * CK, w0, h0, n);
         if (++as == 2) { as = 0; aph ^= 1u; }
-        for (int t = 0; t < ntap; ++t) {
-          const int tap = tap0 + t;
-          const int r = tap / p.R, s = tap % p.R;
+        for (int l = 0; l < loads; ++l) {
+          int cw, chh;
+          if (p.rshift) { cw = w0 + tg - pad; chh = h0 - pad; }
+          else { const int tap = tap0 + l; cw = w0 * p.stride + tap % p.R - pad; chh = h0 * p.stride + tap / p.R - pad; }
           mbar_wait(bar_bempty + 8 * bs, bph ^ 1u);
           mbar_expect_tx(bar_bfull + 8 * bs, B_BYTES);
           for (int c = 0; c < b_chunks; ++c)
-            tma_load_4d(b0 + bs * B_BYTES + c * atom_bytes, &tmX, bar_bfull + 8 * bs, cb * p.cin_blk + c * CK,
-                        w0 * p.stride + s - pad, h0 * p.stride + r - pad, n);
-          if (++bs == WG_B_STAGES) { bs = 0; bph ^= 1u; }
+            tma_load_4d(b0 + bs * B_BYTES + c * b_atom, &tmX, bar_bfull + 8 * bs, cb * p.cin_blk + c * CK, cw, chh, n);
+          if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
         }
       }
     }
@@ -456,19 +464,23 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
       for (int tile = t_beg; tile < t_end; ++tile) {
         mbar_wait(bar_afull + 8 * as, aph);
         tc_fence_after();
-        for (int t = 0; t < ntap; ++t) {
+        for (int l = 0; l < loads; ++l) {
           mbar_wait(bar_bfull + 8 * bs, bph);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.cin_blk);
-          for (int k = 0; k < ksteps; ++k) {
-            // MN-major: LBO = stride between CK-channel atoms, SBO = stride between 8-pixel groups; K advances by
-            // 16 pixel rows = 16*ROWB bytes (a whole number of swizzle atoms).
-            const uint64_t ad = make_desc(a0 + as * A_BYTES + k * 16 * ROWB, atom_bytes, SBO, LAYOUT);
-            const uint64_t bd = make_desc(b0 + bs * B_BYTES + k * 16 * ROWB, atom_bytes, SBO, LAYOUT);
-            tc_mma(d_tmem, ad, bd, idesc, (tile != t_beg || k != 0) ? 1u : 0u);
+          for (int t = 0; t < taps_per_load; ++t) {
+            const int slot = p.rshift ? t : l;                           // accumulator region of this tap
+            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * p.cin_blk);
+            const uint32_t boff = p.rshift ? (uint32_t)(t * p.bw) * ROWB : 0u;   // K offset of tap r inside the halo tile
+            for (int k = 0; k < ksteps; ++k) {
+              // MN-major operands: LBO = stride between CK-channel atoms, SBO = stride between 8-pixel groups; K
+              // advances by 16 pixel rows = 16*ROWB bytes (whole swizzle atoms; r*bw rows too since bw % 8 == 0).
+              const uint64_t ad = make_desc(a0 + as * A_BYTES + k * 16 * ROWB, a_atom, SBO, LAYOUT);
+              const uint64_t bd = make_desc(b0 + bs * B_BYTES + boff + k * 16 * ROWB, b_atom, SBO, LAYOUT);
+              tc_mma(d_tmem, ad, bd, idesc, (tile != t_beg || k != 0) ? 1u : 0u);
+            }
           }
           tc_commit(bar_bempty + 8 * bs);
-          if (++bs == WG_B_STAGES) { bs = 0; bph ^= 1u; }
+          if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
         }
         tc_commit(bar_aempty + 8 * as);
         if (++as == 2) { as = 0; aph ^= 1u; }
@@ -476,21 +488,23 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
       tc_commit(bar_done);
     }
   } else {
-    if (t_beg < t_end) {
-      mbar_wait(bar_done, 0);
-      tc_fence_after();
-      const int q = warp & 3;
-      const int co = mb * 128 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      for (int t = 0; t < ntap; ++t) {
-        for (int c = 0; c < p.cin_blk / 32; ++c) {
-          uint32_t r[32];
-          tc_ld32(taddr + t * p.cin_blk + c * 32, r);
-          if (co < p.Cout) {
-            float* dst = p.dw + ((long long)(tap0 + t) * p.Cout + co) * p.Cin + cb * p.cin_blk + c * 32;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int co = mb * 128 + q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* wsl = p.ws + (long long)ks * p.ws_stride;
+    for (int t = 0; t < ntap; ++t) {
+      const int tap = tap0 + t * tap_step;
+      for (int c = 0; c < p.cin_blk / 32; ++c) {
+        uint32_t r[32];
+        tc_ld32(taddr + t * p.cin_blk + c * 32, r);
+        if (co < p.Cout) {
+          float4* dst = reinterpret_cast<float4*>(wsl + ((long long)tap * p.Cout + co) * p.Cin + cb * p.cin_blk + c * 32);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(r[e]));
-          }
+          for (int e = 0; e < 8; ++e)
+            dst[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
+                                 __uint_as_float(r[4 * e + 3]));
         }
       }
     }
@@ -678,37 +692,88 @@ int svk_conv2d_dgrad_tc(const svk_conv_desc* d, const void* dy, const void* w, v
   return 0;
 }
 
-int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+namespace {
+
+// Pixel tile for wgrad: P = bh*bw a multiple of 16 (UMMA K), <= 128 rows; rshift additionally needs bw % 8 == 0 so that a
+// shift by r*bw rows is a whole number of swizzle atoms.  Cost = smem rows fetched per pixel of work.
+void pick_wgrad_tile(int Ho, int Wo, int es, int rshift, int* bh_out, int* bw_out) {
+  double best = 1e30; int bbh = 0, bbw = 0;
+  const int max_bw = 256 / es;
+  for (int bw = rshift ? 8 : 1; bw <= max_bw && bw <= 128; bw += rshift ? 8 : 1) {
+    for (int bh = 1; bh * bw <= 128 && bh <= Ho + 1; ++bh) {
+      if ((bh * bw) % 16 != 0) continue;
+      if (rshift && (bh + 2) > 256) continue;
+      int th = (Ho + bh - 1) / bh, tw = (Wo + bw - 1) / bw;
+      double rows = (double)th * tw * (bh * bw + (rshift ? (bh + 2) * bw : 3.0 * bh * bw));   // dy + x rows per s
+      double mma = (double)th * tw * bh * bw;
+      double cost = rows + 2.0 * mma;
+      if (cost < best) { best = cost; bbh = bh; bbw = bw; }
+    }
+  }
+  *bh_out = bbh; *bw_out = bbw;
+}
+
+int plan_wgrad(const svk_conv_desc* d, WgradP* pp, int* ck_out, size_t* smem_out) {
+  WgradP& p = *pp;
   SVK_REQUIRE(d->Cin % 32 == 0 && d->Cout % 32 == 0, SVK_E_UNSUPPORTED, "conv2d_wgrad(tc): channels must be multiples of 32");
   const int CK = (d->Cin % 64 == 0 && d->Cout % 64 == 0) ? 64 : 32;
-  WgradP p{};
-  p.stride = d->stride; p.R = d->R; p.Cin = d->Cin; p.Cout = d->Cout; p.ntaps = d->R * d->R; p.dw = dw;
+  p.stride = d->stride; p.R = d->R; p.Cin = d->Cin; p.Cout = d->Cout; p.ntaps = d->R * d->R;
   p.cin_blk = d->Cin < 128 ? d->Cin : 128;
   SVK_REQUIRE(d->Cin % p.cin_blk == 0, SVK_E_UNSUPPORTED, "conv2d_wgrad(tc): Cin=%d unsupported", d->Cin);
   p.n_cin_blk = d->Cin / p.cin_blk;
   p.n_m_blk = (d->Cout + 127) / 128;
-  int max_taps = 512 / p.cin_blk;
-  p.n_tap_grp = (p.ntaps + max_taps - 1) / max_taps;
-  p.taps_per_grp = (p.ntaps + p.n_tap_grp - 1) / p.n_tap_grp;
-  // pixel tile: P = bh*bw multiple of 16; smem = 2 A slots (128 ch) + 3 B slots (cin_blk ch), all P rows
-  int max_rows = 128;
-  int es = d->stride;
-  pick_tile(d->Ho, d->Wo, max_rows, 256 / es, 16, &p.bh, &p.bw);
+  p.rshift = (d->R == 3 && d->stride == 1) ? 1 : 0;
+  if (p.rshift) {
+    p.n_tap_grp = 3; p.taps_per_grp = 3;
+  } else {
+    int max_taps = 512 / p.cin_blk;
+    p.n_tap_grp = (p.ntaps + max_taps - 1) / max_taps;
+    p.taps_per_grp = (p.ntaps + p.n_tap_grp - 1) / p.n_tap_grp;
+  }
+  pick_wgrad_tile(d->Ho, d->Wo, d->stride, p.rshift, &p.bh, &p.bw);
+  SVK_REQUIRE(p.bh > 0, SVK_E_UNSUPPORTED, "conv2d_wgrad(tc): no pixel tile for %dx%d", d->Ho, d->Wo);
   p.P = p.bh * p.bw;
-  SVK_REQUIRE(p.P % 16 == 0 && p.P >= 16, SVK_E_UNSUPPORTED, "conv2d_wgrad(tc): no pixel tile for %dx%d", d->Ho, d->Wo);
+  p.xrows = p.rshift ? (p.bh + 2) * p.bw : p.P;
   p.tiles_h = (d->Ho + p.bh - 1) / p.bh;
   p.tiles_w = (d->Wo + p.bw - 1) / p.bw;
   p.num_pix_tiles = d->N * p.tiles_h * p.tiles_w;
-  int items = p.n_m_blk * p.n_cin_blk * p.n_tap_grp;
+  const int items = p.n_m_blk * p.n_cin_blk * p.n_tap_grp;
   int ks = svk_num_sms() / items;
   if (ks < 1) ks = 1;
   if (ks > p.num_pix_tiles) ks = p.num_pix_tiles;
-  p.ksplit = ks;
+  p.tiles_per = (p.num_pix_tiles + ks - 1) / ks;
+  p.ksplit = (p.num_pix_tiles + p.tiles_per - 1) / p.tiles_per;     // no empty CTA
+  p.ws_stride = (long long)p.ntaps * d->Cout * d->Cin;
+  const size_t a_bytes = (size_t)p.P * CK * 2 * (128 / CK) * 2;
+  const size_t b_slot = (size_t)p.xrows * CK * 2 * (p.cin_blk / CK);
+  p.b_stages = 3;
+  if (a_bytes + 3 * b_slot + 2048 > 200 * 1024) p.b_stages = 2;
+  SVK_REQUIRE(a_bytes + p.b_stages * b_slot + 2048 <= 200 * 1024, SVK_E_UNSUPPORTED, "conv2d_wgrad(tc): tile does not fit smem");
+  *smem_out = a_bytes + p.b_stages * b_slot + 2048;
+  *ck_out = CK;
+  return 0;
+}
+
+}  // namespace
+
+size_t svk_conv2d_wgrad_tc_ws_floats(const svk_conv_desc* d) {
+  WgradP p{}; int ck; size_t smem;
+  if (plan_wgrad(d, &p, &ck, &smem)) return 0;
+  return (size_t)p.ksplit * (size_t)p.ws_stride;
+}
+
+// Writes ksplit partial gradients [ksplit][taps][Cout][Cin] into ws; *ksplit_out tells the caller how many to reduce.
+int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats,
+                        int* ksplit_out, cudaStream_t st) {
+  WgradP p{}; int CK; size_t smem;
+  if (int e = plan_wgrad(d, &p, &CK, &smem)) return e;
+  SVK_REQUIRE((size_t)p.ksplit * (size_t)p.ws_stride <= ws_floats, SVK_E_BADARG,
+              "conv2d_wgrad(tc): workspace too small (%zu floats, need %zu)", ws_floats, (size_t)p.ksplit * (size_t)p.ws_stride);
+  p.ws = ws;
   CUtensorMap tdy, tx;
   if (int e = make_nhwc_map(&tdy, dy, d->N, d->Ho, d->Wo, d->Cout, CK, p.bw, p.bh, 1)) return e;
-  if (int e = make_nhwc_map(&tx, x, d->N, d->H, d->W, d->Cin, CK, p.bw, p.bh, es)) return e;
-  size_t smem = (size_t)p.P * CK * 2 * ((128 / CK) * 2 + (p.cin_blk / CK) * WG_B_STAGES) + 1024 + 1024;
-  int grid = items * ks;
+  if (int e = make_nhwc_map(&tx, x, d->N, d->H, d->W, d->Cin, CK, p.bw, p.rshift ? p.bh + 2 : p.bh, d->stride)) return e;
+  const int grid = p.n_m_blk * p.n_cin_blk * p.n_tap_grp * p.ksplit;
   if (CK == 64) {
     static bool cfg64 = false;
     if (!cfg64) { cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -721,5 +786,6 @@ int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, f
     conv_tc_wgrad_kernel<32><<<grid, TC_THREADS, smem, st>>>(tdy, tx, p);
   }
   SVK_LAUNCH_CHECK("conv_tc_wgrad");
+  *ksplit_out = p.ksplit;
   return 0;
 }

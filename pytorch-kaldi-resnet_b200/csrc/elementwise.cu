@@ -36,24 +36,6 @@ SVK_API int svk_pack_conv_weight(const float* w, void* wf, void* wd, int Cout, i
   SVK_LAUNCH_CHECK("pack_conv_weight");
   return 0;
 }
-__global__ void unpack_dw_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin, int taps) {
-  long long n = (long long)Cout * Cin * taps;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int t = (int)(i % taps);
-    long long r = i / taps;
-    int ci = (int)(r % Cin);
-    int co = (int)(r / Cin);
-    dw[i] = dwp[((long long)t * Cout + co) * Cin + ci];
-  }
-}
-SVK_API int svk_unpack_conv_wgrad(const float* dwp, float* dw, int Cout, int Cin, int R, void* stream) {
-  SVK_REQUIRE(dwp && dw && Cout > 0 && Cin > 0 && (R == 1 || R == 3), SVK_E_BADARG, "unpack_conv_wgrad: bad args");
-  long long n = (long long)Cout * Cin * R * R;
-  unpack_dw_kernel<<<ew_grid(n), EW_THREADS, 0, as_stream(stream)>>>(dwp, dw, Cout, Cin, R * R);
-  SVK_LAUNCH_CHECK("unpack_conv_wgrad");
-  return 0;
-}
-
 // ---------------------------------------------------------------------------------- per-channel reductions
 // Thread (lane_c, lane_r): lane_c = fixed vector of V channels, rows strided.  NACC accumulators per channel.
 template <typename T, int NACC, typename F>

@@ -168,11 +168,10 @@ class SpeakerNetEngine(object):
             nconv = sum(c.cout * c.cin * c.R * c.R for c in self.convs)
             self._wf = torch.empty(nconv, dtype=self.act_dtype, device=dev)
             self._wd = torch.empty(nconv, dtype=self.act_dtype, device=dev)
-            self._dwp = torch.zeros(nconv, dtype=torch.float32, device=dev)
             o = 0
             for c in self.convs:
                 n = c.cout * c.cin * c.R * c.R
-                c.w_fwd, c.w_dgrad, c.dw_packed = self._wf[o:o + n], self._wd[o:o + n], self._dwp[o:o + n]
+                c.w_fwd, c.w_dgrad = self._wf[o:o + n], self._wd[o:o + n]
                 o += n
             nb = len(self.bns)
             self._nbt = torch.zeros(nb, dtype=torch.long, device=dev)
@@ -436,7 +435,6 @@ class SpeakerNetEngine(object):
         ws = sv["ws"]
         B = sv["B"]
         self._bsums.zero_()
-        self._dwp.zero_()
         dlogits = dlogits.contiguous().clone()      # the head backward works in place
         demb = self._head_bwd(dlogits, sv)
         # ---- fc1
@@ -554,10 +552,12 @@ class SpeakerNetEngine(object):
                 p.grad = g
 
     def _wgrad(self, d, conv, x, dy):
-        st = _stream()
-        call.svk_conv2d_wgrad(d, x.data_ptr(), dy.data_ptr(), conv.dw_packed.data_ptr(), st)
-        call.svk_unpack_conv_wgrad(conv.dw_packed.data_ptr(), self._gview[id(conv.mod.weight)].data_ptr(), conv.cout,
-                                   conv.cin, conv.R, st)
+        need = lib.load().svk_conv2d_wgrad_workspace_bytes(d)
+        if need == 0:
+            raise lib.SvkError("svk_conv2d_wgrad_workspace_bytes failed: " + lib.load().svk_last_error_string().decode())
+        ws = self._arena("wgrad_ws", ((need + 3) // 4,), torch.float32)
+        call.svk_conv2d_wgrad(d, x.data_ptr(), dy.data_ptr(), self._gview[id(conv.mod.weight)].data_ptr(), ws.data_ptr(),
+                              ws.numel() * 4, _stream())
 
     def _bucket_done(self, idx):
         if self.grad_ready_cb is not None:

@@ -30,10 +30,9 @@ _D = POINTER(ConvDesc)
 # name -> argtypes, exactly as declared in include/svk.h (tests check every symbol is exported)
 SIGNATURES = {
     "svk_pack_conv_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
-    "svk_unpack_conv_wgrad": [_P, _P, _I, _I, _I, _P],
     "svk_conv2d_fwd": [_D, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
     "svk_conv2d_dgrad": [_D, _P, _P, _P, _P, _P, _P, _P],
-    "svk_conv2d_wgrad": [_D, _P, _P, _P, _P],
+    "svk_conv2d_wgrad": [_D, _P, _P, _P, _P, ctypes.c_size_t, _P],
     "svk_stem_conv_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P],
     "svk_stem_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "svk_channel_stats": [_P, _L, _I, _I, _P, _P],
@@ -80,6 +79,8 @@ def load():
     lib.svk_version.restype = c_int
     lib.svk_last_error_string.restype = c_char_p
     lib.svk_launch_count.restype = c_longlong
+    lib.svk_conv2d_wgrad_workspace_bytes.restype = ctypes.c_size_t
+    lib.svk_conv2d_wgrad_workspace_bytes.argtypes = [_D]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -108,10 +108,11 @@ def conv_wgrad(x_nchw, dy_nchw, r, stride, code, impl):
     d = lib.make_conv_desc(N, H, W, ci, co, r, stride, code, impl)
     x = nhwc(x_nchw, code)
     dy = nhwc(dy_nchw, code)
-    dwp = torch.zeros(r * r * co * ci, dtype=torch.float32, device="cuda")
-    dw = torch.empty(co, ci, r, r, dtype=torch.float32, device="cuda")
-    call.svk_conv2d_wgrad(d, x.data_ptr(), dy.data_ptr(), dwp.data_ptr(), st())
-    call.svk_unpack_conv_wgrad(dwp.data_ptr(), dw.data_ptr(), co, ci, r, st())
+    need = lib.load().svk_conv2d_wgrad_workspace_bytes(d)
+    assert need > 0, lib.load().svk_last_error_string()
+    ws = torch.full(((need + 3) // 4,), float("nan"), dtype=torch.float32, device="cuda")
+    dw = torch.full((co, ci, r, r), float("nan"), dtype=torch.float32, device="cuda")
+    call.svk_conv2d_wgrad(d, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel() * 4, st())
     torch.cuda.synchronize()
     return dw.cpu()
 
