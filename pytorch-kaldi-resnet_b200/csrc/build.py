@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(os.path.dirname(HERE), "svk")
-SOURCES = ["svk_api.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "pool_gemm.cu", "aam_score.cu"]
+SOURCES = ["svk_api.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc3.cu", "pool_gemm.cu", "aam_score.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--extended-lambda", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
 
@@ -19,7 +19,8 @@ def newest(paths):
 def build(force=False, verbose=False):
     out = os.path.join(OUT_DIR, "libsvk.so")
     srcs = [os.path.join(HERE, s) for s in SOURCES]
-    deps = srcs + [os.path.join(HERE, "svk_common.cuh"), os.path.join(HERE, "..", "..", "include", "svk.h")]
+    deps = srcs + [os.path.join(HERE, "svk_common.cuh"), os.path.join(HERE, "tc_common.cuh"),
+                   os.path.join(HERE, "..", "..", "include", "svk.h")]
     if not force and os.path.exists(out) and os.path.getmtime(out) >= newest(deps):
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

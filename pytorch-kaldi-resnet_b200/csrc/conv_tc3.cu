@@ -1,0 +1,224 @@
+// 3x3 / stride-1 fprop and dgrad for the SMALL-channel stages (Cout <= 64: stages 1-2 of ResNet-34, 45 % of the
+// conv FLOPs), where the generic per-tap pipeline of conv_tc.cu is bound by per-stage latency and per-SM L2 ingest
+// rather than by the tensor pipe (profiles/r01_conv_stage1.md).  Two changes of dataflow:
+//   * the whole packed filter (9 * Cin * Cout bf16 <= 96 KB) is loaded into shared memory ONCE per persistent CTA;
+//   * one TMA load fetches a (bh+2) x bw HALO tile for a filter column s; the three taps r = 0,1,2 of that column are
+//     three UMMA A-descriptors into the same tile, offset by r*bw rows (bw % 8 == 0 keeps every offset a whole number of
+//     swizzle atoms).  Per output tile: 3 loads and 0 weight loads instead of 9 + 9.
+// Everything else (TMEM double buffering, epilogue, statistics) is shared with conv_tc.cu.
+#include "tc_common.cuh"
+
+namespace {
+
+struct Gather3P {
+  GatherP g;
+  int col_dw[3];       // W offset of halo load l
+  int row_shift[9];    // [l*3+t]: halo-row offset (0..2) of tap t of load l
+  int wtap[9];         // [l*3+t]: packed-weight tap index
+  int a_stage_bytes;   // halo tile bytes rounded up to 1024
+  int halo_bytes;      // bytes one halo TMA load delivers
+  int n_stages;
+};
+
+template <int KC, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ Gather3P q) {
+  constexpr int ROWB = KC * 2;
+  constexpr int B_BYTES = BN * ROWB;
+  constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
+  constexpr uint32_t SBO = 8 * ROWB;
+  constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+  const GatherP& p = q.g;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_bytes_all = (uint32_t)q.n_stages * q.a_stage_bytes;
+  const uint32_t w_bytes_all = 9u * p.kchunks * B_BYTES;
+  const uint32_t stage0 = base;
+  const uint32_t wsm = base + a_bytes_all;
+  const uint32_t auxoff = a_bytes_all + w_bytes_all;
+  const uint32_t aux = base + auxoff;
+  // aux: full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @144, wfull @160, tmem ptr @176
+  const uint32_t bar_full = aux, bar_empty = aux + 64, bar_tfull = aux + 128, bar_tempty = aux + 144, bar_w = aux + 160;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + auxoff + 176);
+  float* scr = reinterpret_cast<float*>(gbase + auxoff + SMEM_AUX);
+  float* coef = reinterpret_cast<float*>(gbase + auxoff + SMEM_AUX + SCR_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < q.n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (p.scale) {
+    for (int i = threadIdx.x; i < p.Nout; i += TC_THREADS) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, w_bytes_all);
+      for (int t = 0; t < 9; ++t)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_2d(wsm + (t * p.kchunks + kc) * B_BYTES, &tmB, bar_w, kc * KC, t * p.Nout);
+      int stage = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int pt = tile;
+        const int tw = pt % p.tiles_w; pt /= p.tiles_w;
+        const int th = pt % p.tiles_h;
+        const int n = pt / p.tiles_h;
+        const int h0 = th * p.bh, w0 = tw * p.bw;
+        for (int l = 0; l < 3; ++l) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
+            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)q.halo_bytes);
+            tma_load_4d(stage0 + stage * q.a_stage_bytes, &tmA, bar_full + 8 * stage, kc * KC, w0 + q.col_dw[l], h0 - 1, n);
+            if (++stage == q.n_stages) { stage = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      mbar_wait(bar_w, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t aph = 0;
+      const uint32_t row_bytes = (uint32_t)p.bw * ROWB;     // one image row of the halo tile
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t first = 1u;
+        for (int l = 0; l < 3; ++l) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(bar_full + 8 * stage, ph);
+            tc_fence_after();
+            const uint32_t sa = stage0 + stage * q.a_stage_bytes;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              const uint32_t a_t = sa + (uint32_t)q.row_shift[l * 3 + t] * row_bytes;
+              const uint32_t b_t = wsm + (uint32_t)(q.wtap[l * 3 + t] * p.kchunks + kc) * B_BYTES;
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                const uint64_t ad = make_desc(a_t + k * 32, 16, SBO, LAYOUT);
+                const uint64_t bd = make_desc(b_t + k * 32, 16, SBO, LAYOUT);
+                tc_mma(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                first = 0u;
+              }
+            }
+            tc_commit(bar_empty + 8 * stage);
+            if (++stage == q.n_stages) { stage = 0; ph ^= 1u; }
+          }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    gather_epilogue<BN>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int KC, int BN>
+int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const Gather3P& q, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_gather3_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc3: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  int grid = q.g.total_tiles < svk_num_sms() ? q.g.total_tiles : svk_num_sms();
+  conv_tc_gather3_kernel<KC, BN><<<grid, TC_THREADS, smem, st>>>(ta, tb, q);
+  SVK_LAUNCH_CHECK("conv_tc_gather3");
+  return 0;
+}
+
+}  // namespace
+
+// Is the resident-filter halo kernel applicable?  (3x3, stride 1, Cout in {32, 64}, filter fits next to >= 2 stages)
+bool svk_gather3_applicable(int R, int stride, int Kc, int Nout) {
+  if (R != 3 || stride != 1) return false;
+  if (!(Nout == 32 || Nout == 64)) return false;
+  if (Kc % 32 != 0) return false;
+  const int KC = (Kc % 64 == 0) ? 64 : 32;
+  if (!((KC == 32 && (Nout == 32 || Nout == 64)) || (KC == 64 && (Nout == 32 || Nout == 64)))) return false;
+  return (size_t)9 * Kc * Nout * 2 <= 96 * 1024;
+}
+
+// `in` = gathered tensor [N, Hc, Wc, Kc] (x for fprop, dy for dgrad); output grid has the same Hc x Wc (stride 1).
+// dgrad != 0 mirrors the tap offsets (dx[h,w] gathers dy[h+1-r, w+1-s]).
+int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, const void* w_packed, int Nout, int dgrad,
+                             GatherP p, cudaStream_t st) {
+  const int KC = (Kc % 64 == 0) ? 64 : 32;
+  const int BN = Nout;
+  const int ROWB = KC * 2;
+  Gather3P q{};
+  // tile: bw % 8 == 0, bh*bw <= 128; minimise tiles * max(tensor cycles, load cycles + fixed latency)
+  double best = 1e30; int bbh = 0, bbw = 0;
+  const double tensor_cyc = 9.0 * (Kc / 16) * 64.0;
+  for (int bw = 8; bw <= 128; bw += 8) {
+    for (int bh = 1; bh * bw <= 128 && bh <= 254; ++bh) {
+      int th = (Hc + bh - 1) / bh, tw = (Wc + bw - 1) / bw;
+      double load_cyc = 3.0 * (Kc / KC) * ((bh + 2) * bw * ROWB / 48.0 + 250.0);
+      double cost = (double)th * tw * (tensor_cyc > load_cyc ? tensor_cyc : load_cyc);
+      if (cost < best - 1e-9) { best = cost; bbh = bh; bbw = bw; }
+    }
+  }
+  p.bh = bbh; p.bw = bbw;
+  p.tiles_h = (Hc + p.bh - 1) / p.bh;
+  p.tiles_w = (Wc + p.bw - 1) / p.bw;
+  p.num_pix_tiles = N * p.tiles_h * p.tiles_w;
+  p.n_blocks = 1;
+  p.total_tiles = p.num_pix_tiles;
+  p.kchunks = Kc / KC;
+  p.Nout = Nout;
+  p.in_mul = 1;
+  p.Hc = Hc; p.Wc = Wc;
+  q.g = p;
+  for (int l = 0; l < 3; ++l) {
+    q.col_dw[l] = dgrad ? 1 - l : l - 1;             // filter column s = l
+    for (int t = 0; t < 3; ++t) {                     // filter row r = t
+      q.row_shift[l * 3 + t] = dgrad ? 2 - t : t;
+      q.wtap[l * 3 + t] = t * 3 + l;
+    }
+  }
+  q.halo_bytes = (p.bh + 2) * p.bw * ROWB;
+  // the three tap views read rows [shift*bw, shift*bw + 128): keep every stage large enough for the deepest view
+  int need_rows = 2 * p.bw + 128;
+  int rows = (p.bh + 2) * p.bw > need_rows ? (p.bh + 2) * p.bw : need_rows;
+  q.a_stage_bytes = (rows * ROWB + 1023) / 1024 * 1024;
+  const size_t fixed = (size_t)9 * Kc * Nout * 2 + SMEM_AUX + SCR_BYTES + COEF_BYTES + 1024;
+  int ns = (int)((200 * 1024 - fixed) / q.a_stage_bytes);
+  if (ns > 6) ns = 6;
+  SVK_REQUIRE(ns >= 2, SVK_E_UNSUPPORTED, "conv_tc3: not enough shared memory for 2 stages");
+  q.n_stages = ns;
+  const size_t smem = fixed + (size_t)ns * q.a_stage_bytes;
+  CUtensorMap ta, tb;
+  if (int e = make_nhwc_map(&ta, in, N, Hc, Wc, Kc, KC, p.bw, p.bh + 2, 1)) return e;
+  if (int e = make_w_map(&tb, w_packed, (long long)9 * Nout, Kc, KC, BN)) return e;
+  if (KC == 32 && BN == 32) return launch3<32, 32>(ta, tb, q, smem, st);
+  if (KC == 32 && BN == 64) return launch3<32, 64>(ta, tb, q, smem, st);
+  if (KC == 64 && BN == 32) return launch3<64, 32>(ta, tb, q, smem, st);
+  if (KC == 64 && BN == 64) return launch3<64, 64>(ta, tb, q, smem, st);
+  svk_set_error("conv_tc3: no kernel for KC=%d BN=%d", KC, BN);
+  return SVK_E_UNSUPPORTED;
+}

@@ -1,0 +1,280 @@
+// Shared pieces of the tcgen05 convolution kernels: PTX wrappers (mbarrier, TMA, tcgen05), UMMA descriptors, the
+// fprop/dgrad parameter block and epilogue, and the TMA tensor-map builders.
+#pragma once
+#include "svk_common.cuh"
+#include <cuda.h>
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz: protocol bug, do not hang the device
+      printf("svk conv_tc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
+// a_major bit15, b_major bit16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------ fprop / dgrad kernel
+struct GatherP {
+  int Hc, Wc;                 // output class-grid (tile space)
+  int bh, bw, tiles_h, tiles_w, num_pix_tiles, n_blocks, total_tiles;
+  int in_mul;                 // input coordinate = class coordinate * in_mul + tap offset
+  int ntaps;
+  int tap_dh[9], tap_dw[9], tap_w[9];
+  int kchunks;                // Kc / KC
+  int Nout;                   // output channels (row pitch of out)
+  int Hout, Wout, o_mul, o_off_h, o_off_w;   // out pixel = (i*o_mul + o_off_h, j*o_mul + o_off_w)
+  bf16* out;
+  const float* scale; const float* shift;
+  const bf16* res; const bf16* res_m; const bf16* mask;
+  int relu;
+  const int* valid_w;
+  double* stats;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int SMEM_AUX = 1024;                 // barriers + tmem pointer
+constexpr int SCR_BYTES = 4 * 32 * 33 * 4;     // per-epilogue-warp transpose scratch
+constexpr int COEF_BYTES = 2 * 512 * 4;        // scale/shift staged in smem (Nout <= 512)
+
+// Epilogue of the gather kernels (4 warps): TMEM -> registers -> scale/shift -> +residual -> ReLU -> bf16 -> global, plus the
+// per-channel sum / sum-of-squares of the stored values (BatchNorm batch statistics) reduced through smem.
+template <int BN>
+__device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
+                                                float* scr, const float* coef, int warp, int lane) {
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    float* myscr = scr + (warp - 2) * 32 * 33;
+    constexpr int NCH = BN / 32;
+    float s1[NCH], s2[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+    int stat_blk = -1;
+    int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nblk = tile % p.n_blocks;
+      int pt = tile / p.n_blocks;
+      const int tw = pt % p.tiles_w; pt /= p.tiles_w;
+      const int th = pt % p.tiles_h;
+      const int n = pt / p.tiles_h;
+      if (p.stats && stat_blk != nblk) {
+        if (stat_blk >= 0) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            atomicAdd(&p.stats[stat_blk * BN + c * 32 + lane], (double)s1[c]);
+            atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + lane], (double)s2[c]);
+            s1[c] = 0.f; s2[c] = 0.f;
+          }
+        }
+        stat_blk = nblk;
+      }
+      const int m = q * 32 + lane;          // accumulator row = pixel index inside the tile
+      const int i = m / p.bw, j = m - i * p.bw;
+      const int hc = th * p.bh + i, wc = tw * p.bw + j;
+      bool valid = (i < p.bh) && (hc < p.Hc) && (wc < p.Wc);
+      const int oh = hc * p.o_mul + p.o_off_h, ow = wc * p.o_mul + p.o_off_w;
+      const long long off = valid ? ((((long long)n * p.Hout + oh) * p.Wout + ow) * p.Nout + nblk * BN) : 0;
+      bool zero_out = false;
+      if (valid && p.valid_w) zero_out = ow >= p.valid_w[n];
+
+      mbar_wait(bar_tfull + 8 * acc, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t r[32];
+        tc_ld32(taddr + c * 32, r);
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+        if (p.scale) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaf(v[e], coef[nblk * BN + c * 32 + e], coef[512 + nblk * BN + c * 32 + e]);
+        }
+        if (valid) {
+          if (p.res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float t8[8];
+              Vec<bf16>::load(p.res + off + c * 32 + g * 8, t8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[g * 8 + e] += t8[e];
+            }
+          }
+          if (p.res_m) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float t8[8], k8[8];
+              Vec<bf16>::load(p.res_m + off + c * 32 + g * 8, t8);
+              Vec<bf16>::load(p.mask + off + c * 32 + g * 8, k8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[g * 8 + e] += (k8[e] > 0.f) ? t8[e] : 0.f;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+        if (zero_out) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0.f;
+        }
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float t8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t8[e] = v[g * 8 + e];
+            Vec<bf16>::store(p.out + off + c * 32 + g * 8, t8);
+          }
+        }
+        if (p.stats) {
+          // statistics of the values as stored (bf16-rounded); transpose through smem so lane e owns channel e
+#pragma unroll
+          for (int e = 0; e < 32; ++e) myscr[lane * 33 + e] = valid ? round_to<bf16>(v[e]) : 0.f;
+          __syncwarp();
+          float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) { float x = myscr[rr * 33 + lane]; a1 += x; a2 = fmaf(x, x, a2); }
+          s1[c] += a1; s2[c] += a2;
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; aph ^= 1u; }
+    }
+    if (p.stats && stat_blk >= 0) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        atomicAdd(&p.stats[stat_blk * BN + c * 32 + lane], (double)s1[c]);
+        atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + lane], (double)s2[c]);
+      }
+    }
+  }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 4-D map over an NHWC bf16 tensor; box = {ck channels, bw*es, bh*es, 1}, element strides {1, es, es, 1}.
+inline int make_nhwc_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int ck, int bw, int bh, int es) {
+  EncodeTiledFn enc = get_encode();
+  SVK_REQUIRE(enc, SVK_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)ck, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  SVK_REQUIRE(box[1] <= 256 && box[2] <= 256, SVK_E_UNSUPPORTED, "conv_tc: TMA box %ux%u too large", box[1], box[2]);
+  CUtensorMapSwizzle sw = (ck == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SVK_REQUIRE(r == CUDA_SUCCESS, SVK_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled(NHWC) failed with %d", (int)r);
+  return 0;
+}
+// 2-D map over packed weights [rows][K] bf16; box = {ck, bn}.
+inline int make_w_map(CUtensorMap* m, const void* ptr, long long rows, int K, int ck, int bn) {
+  EncodeTiledFn enc = get_encode();
+  SVK_REQUIRE(enc, SVK_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)ck, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = (ck == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SVK_REQUIRE(r == CUDA_SUCCESS, SVK_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+  return 0;
+}
+
+}  // namespace
