@@ -44,6 +44,8 @@ def build(force=False, verbose=False):
     if verbose:
         print("\n".join(log))
     subprocess.check_call([nvcc, "-shared", "-o", out] + objs + ["-lcudart"])
+    import ctypes
+    ctypes.CDLL(out)          # fail here, not on the GPU box, if a symbol is unresolved
     return out
 
 

@@ -4,9 +4,28 @@
 #include "svk_common.cuh"
 #include <cuda.h>
 
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------ fprop / dgrad kernel
+struct GatherP {
+  int Hc, Wc;                 // output class-grid (tile space)
+  int bh, bw, tiles_h, tiles_w, num_pix_tiles, n_blocks, total_tiles;
+  int in_mul;                 // input coordinate = class coordinate * in_mul + tap offset
+  int ntaps;
+  int tap_dh[9], tap_dw[9], tap_w[9];
+  int kchunks;                // Kc / KC
+  int Nout;                   // output channels (row pitch of out)
+  int Hout, Wout, o_mul, o_off_h, o_off_w;   // out pixel = (i*o_mul + o_off_h, j*o_mul + o_off_w)
+  bf16* out;
+  const float* scale; const float* shift;
+  const bf16* res; const bf16* res_m; const bf16* mask;
+  int relu;
+  const int* valid_w;
+  double* stats;
+};
+
 namespace {
 
-typedef __nv_bfloat16 bf16;
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,23 +111,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ------------------------------------------------------------------------------------------ fprop / dgrad kernel
-struct GatherP {
-  int Hc, Wc;                 // output class-grid (tile space)
-  int bh, bw, tiles_h, tiles_w, num_pix_tiles, n_blocks, total_tiles;
-  int in_mul;                 // input coordinate = class coordinate * in_mul + tap offset
-  int ntaps;
-  int tap_dh[9], tap_dw[9], tap_w[9];
-  int kchunks;                // Kc / KC
-  int Nout;                   // output channels (row pitch of out)
-  int Hout, Wout, o_mul, o_off_h, o_off_w;   // out pixel = (i*o_mul + o_off_h, j*o_mul + o_off_w)
-  bf16* out;
-  const float* scale; const float* shift;
-  const bf16* res; const bf16* res_m; const bf16* mask;
-  int relu;
-  const int* valid_w;
-  double* stats;
-};
 
 constexpr int TC_THREADS = 192;
 constexpr int SMEM_AUX = 1024;                 // barriers + tmem pointer
