@@ -98,9 +98,13 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
+      // descriptors are base + (byte offset >> 4): nothing is rebuilt inside the loop (the issuing thread is
+      // instruction-latency bound, profiles/r01_conv_stage1.md)
       constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
       int stage = 0; uint32_t ph = 0;
       int acc = 0; uint32_t aph = 0;
+      const uint64_t a_desc0 = make_desc(stage0, 16, Cfg::SBO, Cfg::LAYOUT);
+      uint64_t a_desc = a_desc0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
         tc_fence_after();
@@ -108,15 +112,13 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(bar_full + 8 * stage, ph);
           tc_fence_after();
-          const uint32_t sa = stage0 + stage * Cfg::STAGE;
+          const uint64_t b_desc = a_desc + (uint64_t)(Cfg::A_BYTES >> 4);
+          tc_mma(d_tmem, a_desc, b_desc, idesc, ks != 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            const uint64_t ad = make_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-            const uint64_t bd = make_desc(sa + Cfg::A_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-            tc_mma(d_tmem, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 1; k < KC / 16; ++k) tc_mma(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
           tc_commit(bar_empty + 8 * stage);
-          if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; }
+          a_desc += (uint64_t)(Cfg::STAGE >> 4);
+          if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; a_desc = a_desc0; }
         }
         tc_commit(bar_tfull + 8 * acc);
         if (++acc == 2) { acc = 0; aph ^= 1u; }
@@ -252,12 +254,15 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
             const int slot = p.rshift ? t : l;                           // accumulator region of this tap
             const uint32_t d_tmem = tmem_base + (uint32_t)(slot * p.cin_blk);
             const uint32_t boff = p.rshift ? (uint32_t)(t * p.bw) * ROWB : 0u;   // K offset of tap r inside the halo tile
-            for (int k = 0; k < ksteps; ++k) {
-              // MN-major operands: LBO = stride between CK-channel atoms, SBO = stride between 8-pixel groups; K
-              // advances by 16 pixel rows = 16*ROWB bytes (whole swizzle atoms; r*bw rows too since bw % 8 == 0).
-              const uint64_t ad = make_desc(a0 + as * A_BYTES + k * 16 * ROWB, a_atom, SBO, LAYOUT);
-              const uint64_t bd = make_desc(b0 + bs * B_BYTES + boff + k * 16 * ROWB, b_atom, SBO, LAYOUT);
-              tc_mma(d_tmem, ad, bd, idesc, (tile != t_beg || k != 0) ? 1u : 0u);
+            // MN-major operands: LBO = stride between CK-channel atoms, SBO = stride between 8-pixel groups; K
+            // advances by 16 pixel rows = 16*ROWB bytes (whole swizzle atoms; r*bw rows too since bw % 8 == 0).
+            // Descriptors are built once per tap and advanced by adding (16*ROWB) >> 4 = ROWB to the address field.
+            uint64_t ad = make_desc(a0 + as * A_BYTES, a_atom, SBO, LAYOUT);
+            uint64_t bd = make_desc(b0 + bs * B_BYTES + boff, b_atom, SBO, LAYOUT);
+            tc_mma(d_tmem, ad, bd, idesc, tile != t_beg ? 1u : 0u);
+            for (int k = 1; k < ksteps; ++k) {
+              ad += ROWB; bd += ROWB;
+              tc_mma(d_tmem, ad, bd, idesc, 1u);
             }
           }
           tc_commit(bar_bempty + 8 * bs);

@@ -12,15 +12,15 @@ namespace {
 
 struct Gather3P {
   GatherP g;
-  int col_dw[3];       // W offset of halo load l
-  int row_shift[9];    // [l*3+t]: halo-row offset (0..2) of tap t of load l
-  int wtap[9];         // [l*3+t]: packed-weight tap index
+  int col_dw[3];       // W offset of halo load l (filter column s = l): l-1 for fprop, 1-l for dgrad
   int a_stage_bytes;   // halo tile bytes rounded up to 1024
   int halo_bytes;      // bytes one halo TMA load delivers
   int n_stages;
 };
 
-template <int KC, int BN>
+// Kc == KC (one K chunk per tap: Cin in {32, 64}).  Tap (r = t, s = l) reads halo rows shifted by t (fprop) or 2 - t (dgrad)
+// and the packed filter tap t*3 + l.
+template <int KC, int BN, bool DGRAD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ Gather3P q) {
@@ -34,7 +34,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t a_bytes_all = (uint32_t)q.n_stages * q.a_stage_bytes;
-  const uint32_t w_bytes_all = 9u * p.kchunks * B_BYTES;
+  const uint32_t w_bytes_all = 9u * B_BYTES;
   const uint32_t stage0 = base;
   const uint32_t wsm = base + a_bytes_all;
   const uint32_t auxoff = a_bytes_all + w_bytes_all;
@@ -68,9 +68,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_expect_tx(bar_w, w_bytes_all);
-      for (int t = 0; t < 9; ++t)
-        for (int kc = 0; kc < p.kchunks; ++kc)
-          tma_load_2d(wsm + (t * p.kchunks + kc) * B_BYTES, &tmB, bar_w, kc * KC, t * p.Nout);
+      for (int t = 0; t < 9; ++t) tma_load_2d(wsm + t * B_BYTES, &tmB, bar_w, 0, t * p.Nout);
       int stage = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int pt = tile;
@@ -78,50 +76,50 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int th = pt % p.tiles_h;
         const int n = pt / p.tiles_h;
         const int h0 = th * p.bh, w0 = tw * p.bw;
+#pragma unroll
         for (int l = 0; l < 3; ++l) {
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
-            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)q.halo_bytes);
-            tma_load_4d(stage0 + stage * q.a_stage_bytes, &tmA, bar_full + 8 * stage, kc * KC, w0 + q.col_dw[l], h0 - 1, n);
-            if (++stage == q.n_stages) { stage = 0; ph ^= 1u; }
-          }
+          mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
+          mbar_expect_tx(bar_full + 8 * stage, (uint32_t)q.halo_bytes);
+          tma_load_4d(stage0 + stage * q.a_stage_bytes, &tmA, bar_full + 8 * stage, 0, w0 + (DGRAD ? 1 - l : l - 1), h0 - 1, n);
+          if (++stage == q.n_stages) { stage = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
+      // The issuing thread is instruction-latency bound (profiles/r01: ~180 cycles per UMMA against a 64-cycle tensor
+      // floor when descriptors are rebuilt per MMA), so everything is hoisted: a descriptor is base + (byte offset >> 4)
+      // in its low 14-bit address field, and all tap offsets are compile-time multiples of loop-invariant registers.
       constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
       mbar_wait(bar_w, 0);
       tc_fence_after();
       int stage = 0; uint32_t ph = 0;
       int acc = 0; uint32_t aph = 0;
-      const uint32_t row_bytes = (uint32_t)p.bw * ROWB;     // one image row of the halo tile
+      const uint64_t row16 = (uint64_t)(((uint32_t)p.bw * ROWB) >> 4);      // one halo image row, in 16-byte units
+      const uint64_t a_desc0 = make_desc(stage0, 16, SBO, LAYOUT);
+      const uint64_t a_stage16 = (uint64_t)((uint32_t)q.a_stage_bytes >> 4);
+      const uint64_t b_desc0 = make_desc(wsm, 16, SBO, LAYOUT);
+      uint64_t a_desc = a_desc0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        uint32_t first = 1u;
+#pragma unroll
         for (int l = 0; l < 3; ++l) {
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(bar_full + 8 * stage, ph);
-            tc_fence_after();
-            const uint32_t sa = stage0 + stage * q.a_stage_bytes;
+          mbar_wait(bar_full + 8 * stage, ph);
+          tc_fence_after();
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-              const uint32_t a_t = sa + (uint32_t)q.row_shift[l * 3 + t] * row_bytes;
-              const uint32_t b_t = wsm + (uint32_t)(q.wtap[l * 3 + t] * p.kchunks + kc) * B_BYTES;
+          for (int t = 0; t < 3; ++t) {
+            const uint64_t ad_t = a_desc + (uint64_t)(DGRAD ? 2 - t : t) * row16;
+            const uint64_t bd_t = b_desc0 + (uint64_t)(((t * 3 + l) * B_BYTES) >> 4);
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-                const uint64_t ad = make_desc(a_t + k * 32, 16, SBO, LAYOUT);
-                const uint64_t bd = make_desc(b_t + k * 32, 16, SBO, LAYOUT);
-                tc_mma(d_tmem, ad, bd, idesc, first ? 0u : 1u);
-                first = 0u;
-              }
-            }
-            tc_commit(bar_empty + 8 * stage);
-            if (++stage == q.n_stages) { stage = 0; ph ^= 1u; }
+            for (int k = 0; k < KC / 16; ++k)
+              tc_mma(d_tmem, ad_t + 2 * k, bd_t + 2 * k, idesc, (l | t | k) != 0 ? 1u : 0u);
           }
+          tc_commit(bar_empty + 8 * stage);
+          a_desc += a_stage16;
+          if (++stage == q.n_stages) { stage = 0; ph ^= 1u; a_desc = a_desc0; }
         }
         tc_commit(bar_tfull + 8 * acc);
         if (++acc == 2) { acc = 0; aph ^= 1u; }
@@ -138,16 +136,16 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
-template <int KC, int BN>
+template <int KC, int BN, bool DGRAD>
 int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const Gather3P& q, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_gather3_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_gather3_kernel<KC, BN, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc3: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     configured = true;
   }
   int grid = q.g.total_tiles < svk_num_sms() ? q.g.total_tiles : svk_num_sms();
-  conv_tc_gather3_kernel<KC, BN><<<grid, TC_THREADS, smem, st>>>(ta, tb, q);
+  conv_tc_gather3_kernel<KC, BN, DGRAD><<<grid, TC_THREADS, smem, st>>>(ta, tb, q);
   SVK_LAUNCH_CHECK("conv_tc_gather3");
   return 0;
 }
@@ -158,17 +156,14 @@ int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const Gather3P& q, siz
 bool svk_gather3_applicable(int R, int stride, int Kc, int Nout) {
   if (R != 3 || stride != 1) return false;
   if (!(Nout == 32 || Nout == 64)) return false;
-  if (Kc % 32 != 0) return false;
-  const int KC = (Kc % 64 == 0) ? 64 : 32;
-  if (!((KC == 32 && (Nout == 32 || Nout == 64)) || (KC == 64 && (Nout == 32 || Nout == 64)))) return false;
-  return (size_t)9 * Kc * Nout * 2 <= 96 * 1024;
+  return Kc == 32 || Kc == 64;        // one K chunk per tap; the filter (<= 73.7 KB) stays resident in smem
 }
 
 // `in` = gathered tensor [N, Hc, Wc, Kc] (x for fprop, dy for dgrad); output grid has the same Hc x Wc (stride 1).
 // dgrad != 0 mirrors the tap offsets (dx[h,w] gathers dy[h+1-r, w+1-s]).
 int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, const void* w_packed, int Nout, int dgrad,
                              GatherP p, cudaStream_t st) {
-  const int KC = (Kc % 64 == 0) ? 64 : 32;
+  const int KC = Kc;
   const int BN = Nout;
   const int ROWB = KC * 2;
   Gather3P q{};
@@ -194,13 +189,7 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   p.in_mul = 1;
   p.Hc = Hc; p.Wc = Wc;
   q.g = p;
-  for (int l = 0; l < 3; ++l) {
-    q.col_dw[l] = dgrad ? 1 - l : l - 1;             // filter column s = l
-    for (int t = 0; t < 3; ++t) {                     // filter row r = t
-      q.row_shift[l * 3 + t] = dgrad ? 2 - t : t;
-      q.wtap[l * 3 + t] = t * 3 + l;
-    }
-  }
+  for (int l = 0; l < 3; ++l) q.col_dw[l] = dgrad ? 1 - l : l - 1;
   q.halo_bytes = (p.bh + 2) * p.bw * ROWB;
   // the three tap views read rows [shift*bw, shift*bw + 128): keep every stage large enough for the deepest view
   int need_rows = 2 * p.bw + 128;
@@ -215,10 +204,9 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   CUtensorMap ta, tb;
   if (int e = make_nhwc_map(&ta, in, N, Hc, Wc, Kc, KC, p.bw, p.bh + 2, 1)) return e;
   if (int e = make_w_map(&tb, w_packed, (long long)9 * Nout, Kc, KC, BN)) return e;
-  if (KC == 32 && BN == 32) return launch3<32, 32>(ta, tb, q, smem, st);
-  if (KC == 32 && BN == 64) return launch3<32, 64>(ta, tb, q, smem, st);
-  if (KC == 64 && BN == 32) return launch3<64, 32>(ta, tb, q, smem, st);
-  if (KC == 64 && BN == 64) return launch3<64, 64>(ta, tb, q, smem, st);
+#define SVK_L3(K_, N_) if (KC == K_ && BN == N_) return dgrad ? launch3<K_, N_, true>(ta, tb, q, smem, st) : launch3<K_, N_, false>(ta, tb, q, smem, st)
+  SVK_L3(32, 32); SVK_L3(32, 64); SVK_L3(64, 32); SVK_L3(64, 64);
+#undef SVK_L3
   svk_set_error("conv_tc3: no kernel for KC=%d BN=%d", KC, BN);
   return SVK_E_UNSUPPORTED;
 }
