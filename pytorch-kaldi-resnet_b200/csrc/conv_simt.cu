@@ -2,6 +2,7 @@
 // This is the fp32 VALIDATION-mode path (north-star: "<=1e-4 relative in an fp32 validation mode") and the
 // on-device cross-check for the tcgen05 kernels in conv_tc.cu; it is not the product path for bf16.
 #include "svk_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -288,6 +289,16 @@ int svk_conv2d_dgrad_tc(const svk_conv_desc* d, const void* dy, const void* w, v
 int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats, int* ksplit_out,
                         cudaStream_t st);
 size_t svk_conv2d_wgrad_tc_ws_floats(const svk_conv_desc* d);
+// implemented in conv_tc_wgrad3.cu (3x3/s1, Cin == Cout in {32, 64}: taps stacked along M)
+bool svk_wgrad3_applicable(const svk_conv_desc* d);
+size_t svk_conv2d_wgrad3_tc_ws_floats(const svk_conv_desc* d);
+int svk_conv2d_wgrad3_tc(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats, int* ksplit_out,
+                         cudaStream_t st);
+static bool wgrad3_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVK_DISABLE_WGRAD3"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
 
 SVK_API int svk_conv2d_fwd(const svk_conv_desc* d, const void* x, const void* w, void* y, double* stats,
                            const float* scale, const float* shift, const void* residual, int relu,
@@ -324,7 +335,10 @@ SVK_API int svk_conv2d_dgrad(const svk_conv_desc* d, const void* dy, const void*
 
 SVK_API size_t svk_conv2d_wgrad_workspace_bytes(const svk_conv_desc* d) {
   if (check_desc("conv2d_wgrad_workspace_bytes", d)) return 0;
-  if (d->impl == SVK_IMPL_TCGEN05) return svk_conv2d_wgrad_tc_ws_floats(d) * sizeof(float);
+  if (d->impl == SVK_IMPL_TCGEN05) {
+    if (wgrad3_enabled() && svk_wgrad3_applicable(d)) return svk_conv2d_wgrad3_tc_ws_floats(d) * sizeof(float);
+    return svk_conv2d_wgrad_tc_ws_floats(d) * sizeof(float);
+  }
   long long ks; int gz;
   simt_wgrad_plan(d, &ks, &gz);
   return (size_t)gz * d->R * d->R * d->Cout * d->Cin * sizeof(float);
@@ -339,7 +353,11 @@ SVK_API int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* 
   int ksplit = 0;
   if (d->impl == SVK_IMPL_TCGEN05) {
     SVK_REQUIRE(d->dtype == SVK_BF16, SVK_E_UNSUPPORTED, "conv2d_wgrad: tcgen05 path is bf16 only");
-    if (int e = svk_conv2d_wgrad_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
+    if (wgrad3_enabled() && svk_wgrad3_applicable(d)) {
+      if (int e = svk_conv2d_wgrad3_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
+    } else {
+      if (int e = svk_conv2d_wgrad_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
+    }
   } else {
     SVK_REQUIRE(d->impl == SVK_IMPL_SIMT, SVK_E_BADARG, "conv2d_wgrad: bad impl %d", d->impl);
     if (int e = svk_conv2d_wgrad_simt(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;

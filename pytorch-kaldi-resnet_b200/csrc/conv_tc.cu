@@ -35,7 +35,7 @@ struct GatherCfg {
 };
 
 template <int KC, int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(GATHER_THREADS, 1)
 conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ GatherP p) {
   typedef GatherCfg<KC, BN> Cfg;
@@ -58,7 +58,7 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (p.scale) {
-    for (int i = threadIdx.x; i < p.Nout; i += TC_THREADS) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
+    for (int i = threadIdx.x; i < p.Nout; i += GATHER_THREADS) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(Cfg::TMEM_COLS) : "memory");
@@ -331,7 +331,7 @@ int launch_gather_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP&
     configured = true;
   }
   int grid = p.total_tiles < svk_num_sms() ? p.total_tiles : svk_num_sms();
-  conv_tc_gather_kernel<KC, BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
+  conv_tc_gather_kernel<KC, BN><<<grid, GATHER_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
   SVK_LAUNCH_CHECK("conv_tc_gather");
   return 0;
 }

@@ -21,7 +21,7 @@ struct Gather3P {
 // Kc == KC (one K chunk per tap: Cin in {32, 64}).  Tap (r = t, s = l) reads halo rows shifted by t (fprop) or 2 - t (dgrad)
 // and the packed filter tap t*3 + l.
 template <int KC, int BN, bool DGRAD>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(GATHER_THREADS, 1)
 conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ Gather3P q) {
   constexpr int ROWB = KC * 2;
@@ -53,7 +53,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (p.scale) {
-    for (int i = threadIdx.x; i < p.Nout; i += TC_THREADS) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
+    for (int i = threadIdx.x; i < p.Nout; i += GATHER_THREADS) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
@@ -145,7 +145,7 @@ int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const Gather3P& q, siz
     configured = true;
   }
   int grid = q.g.total_tiles < svk_num_sms() ? q.g.total_tiles : svk_num_sms();
-  conv_tc_gather3_kernel<KC, BN, DGRAD><<<grid, TC_THREADS, smem, st>>>(ta, tb, q);
+  conv_tc_gather3_kernel<KC, BN, DGRAD><<<grid, GATHER_THREADS, smem, st>>>(ta, tb, q);
   SVK_LAUNCH_CHECK("conv_tc_gather3");
   return 0;
 }

@@ -112,9 +112,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
 }
 
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;                // wgrad kernels: producer warp, MMA warp, 4 epilogue warps
+constexpr int GATHER_THREADS = 320;            // fprop/dgrad kernels: producer, MMA, 2 x 4 epilogue warps (one group per
+                                               // TMEM accumulator buffer: a tile's epilogue is latency-bound, ~2x the MMA time)
 constexpr int SMEM_AUX = 1024;                 // barriers + tmem pointer
-constexpr int SCR_BYTES = 4 * 32 * 33 * 4;     // per-epilogue-warp transpose scratch
+constexpr int SCR_BYTES = 8 * 32 * 33 * 4;     // per-epilogue-warp transpose scratch
 constexpr int COEF_BYTES = 2 * 512 * 4;        // scale/shift staged in smem (Nout <= 512)
 
 // Epilogue of the gather kernels (4 warps): TMEM -> registers -> scale/shift -> +residual -> ReLU -> bf16 -> global, plus the
@@ -123,14 +125,17 @@ template <int BN>
 __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
                                                 float* scr, const float* coef, int warp, int lane) {
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int group = (warp - 2) >> 2;      // epilogue group g drains accumulator buffer g = every other tile of this CTA
     float* myscr = scr + (warp - 2) * 32 * 33;
     constexpr int NCH = BN / 32;
     float s1[NCH], s2[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
     int stat_blk = -1;
-    int acc = 0; uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int acc = group; uint32_t aph = 0;
+    const int m = q * 32 + lane;            // accumulator row = pixel index inside the tile (loop invariant)
+    const int i = m / p.bw, j = m - i * p.bw;
+    for (int tile = blockIdx.x + group * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
       const int nblk = tile % p.n_blocks;
       int pt = tile / p.n_blocks;
       const int tw = pt % p.tiles_w; pt /= p.tiles_w;
@@ -147,8 +152,6 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
         }
         stat_blk = nblk;
       }
-      const int m = q * 32 + lane;          // accumulator row = pixel index inside the tile
-      const int i = m / p.bw, j = m - i * p.bw;
       const int hc = th * p.bh + i, wc = tw * p.bw + j;
       bool valid = (i < p.bh) && (hc < p.Hc) && (wc < p.Wc);
       const int oh = hc * p.o_mul + p.o_off_h, ow = wc * p.o_mul + p.o_off_w;
@@ -223,7 +226,7 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      if (++acc == 2) { acc = 0; aph ^= 1u; }
+      aph ^= 1u;
     }
     if (p.stats && stat_blk >= 0) {
 #pragma unroll
