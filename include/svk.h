@@ -75,6 +75,12 @@ int svk_conv2d_fwd(const svk_conv_desc* d, const void* x, const void* w_fwd, voi
  * (dy is N,Ho,Wo,Cout; dx is N,H,W,Cin).  replaces: cuDNN dgrad under loss.backward(), train_resnet.py:327. */
 int svk_conv2d_dgrad(const svk_conv_desc* d, const void* dy, const void* w_dgrad, void* dx, const void* res,
                      const void* res_m, const void* mask, void* stream);
+/* All convs of a network in ONE launch: table[nconv][6] (int64, device) = {offset of the OIHW weight in `flat_params`
+ * (floats), offset of its packed copies in w_fwd/w_dgrad (elements), Cout, Cin, R*R, cumulative element start};
+ * total = sum Cout*Cin*R*R.  Same layouts as svk_pack_conv_weight. */
+int svk_pack_conv_weights_batched(const float* flat_params, void* w_fwd, void* w_dgrad, const long long* table, int nconv,
+                                  long long total, int dtype, void* stream);
+
 /* dw_oihw[Cout][Cin][R][R] (fp32, overwritten) = dy^T * im2col(x).  Split-K over pixel tiles: every CTA writes its
  * partial sum into `workspace` with plain stores, then one reduction kernel sums the partials in a fixed order and
  * transposes to OIHW (deterministic, no atomics).  workspace_bytes >= svk_conv2d_wgrad_workspace_bytes(d).
@@ -99,6 +105,14 @@ int svk_channel_stats(const void* x, long long M, int C, int dtype, double* stat
 int svk_bn_finalize(const double* stats, long long M, int C, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                     float* save_mean, float* save_rstd, void* stream);
+/* Training-mode BN finalise + apply in one pass: out = act(bn(x) + R), R = 0 | res | bn_b(res) (downsample branch).
+ * Every thread derives the coefficients of its channels from the fp64 sums; the first threads also publish
+ * coef[0..3][cstride] = scale, shift, mean, rstd (kept for backward) and update the running statistics exactly like
+ * svk_bn_finalize.  replaces: model.py:52-53, :56-62 (+ :233-236 downsample BN) in training mode. */
+int svk_bn_train_act_fwd(const void* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float* coef, const void* res, const double* stats_b, const float* gamma_b,
+                         const float* beta_b, float* running_mean_b, float* running_var_b, float* coef_b, int cstride,
+                         float momentum, float eps, int relu, void* out, long long M, int C, int dtype, void* stream);
 /* Eval-mode BN coefficients from running stats: scale = gamma/sqrt(rv+eps), shift = beta - rm*scale. */
 int svk_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                        float eps, int C, float* scale, float* shift, void* stream);

@@ -424,38 +424,44 @@ SVK_API int svk_stem_conv_fwd(const float* x, const float* w, void* y, int N, in
   return 0;
 }
 
-// dw[co][tap] = sum_p dy[p, co] * x[p + shift(tap)].  Block = (CO channels) x (256/CO pixel lanes); per-block partials
-// are combined with fp32 atomics into dw (zeroed here first by a memset node).
+// dw[co][tap] = sum_p dy[p, co] * x[p + shift(tap)].  Thread = (pixel lane, group of V channels): one 16-byte load of
+// dy per pixel, the 9 shifted inputs from L1, 9*V accumulators in registers; warp-shuffle + smem reduction, one fp32
+// atomic per (channel, tap) per block.  HBM-bound on dy (2*Cout bytes per pixel).
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                          float* __restrict__ dw, int N, int H, int W, int CO) {
-  const int c = threadIdx.x % CO, lane_p = threadIdx.x / CO, lanes = blockDim.x / CO;
+  constexpr int V = Vec<T>::N;
+  const int groups = CO / V;                                  // channel groups per pixel (4 or 8 for bf16)
+  const int cg = threadIdx.x % groups, lane_p = threadIdx.x / groups, lanes = blockDim.x / groups;
   long long total = (long long)N * H * W;
-  float acc[9];
+  float acc[9][V];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[k][i] = 0.f;
   for (long long p = (long long)blockIdx.x * lanes + lane_p; p < total; p += (long long)gridDim.x * lanes) {
     int wq = (int)(p % W); long long q = p / W; int h = (int)(q % H);
-    float g = to_f(dy[p * CO + c]);
+    float g[V];
+    Vec<T>::load(dy + p * CO + cg * V, g);
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         int ih = h + r - 1, iw = wq + s - 1;
         float xv = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? x[p + (long long)(r - 1) * W + (s - 1)] : 0.f;
-        acc[r * 3 + s] = fmaf(g, xv, acc[r * 3 + s]);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[r * 3 + s][i] = fmaf(g[i], xv, acc[r * 3 + s][i]);
       }
   }
-  __shared__ float red[256 * 9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) red[threadIdx.x * 9 + k] = acc[k];
+  __shared__ float red[64 * 9];                               // CO <= 64
+  for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  for (int o = threadIdx.x; o < CO * 9; o += blockDim.x) {
-    int cc = o / 9, k = o % 9;
-    float s = 0.f;
-    for (int l = 0; l < lanes; ++l) s += red[(l * CO + cc) * 9 + k];
-    atomicAdd(&dw[o], s);
-  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) atomicAdd(&red[(cg * V + i) * 9 + k], acc[k][i]);
+  __syncthreads();
+  for (int o = threadIdx.x; o < CO * 9; o += blockDim.x) atomicAdd(&dw[o], red[o]);
 }
 SVK_API int svk_stem_conv_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int Cout, int dtype,
                                 void* stream) {
@@ -465,8 +471,8 @@ SVK_API int svk_stem_conv_wgrad(const float* x, const void* dy, float* dw, int N
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * Cout * 9, st);
   SVK_REQUIRE(e == cudaSuccess, (int)e, "stem_conv_wgrad: memset failed: %s", cudaGetErrorString(e));
   long long total = (long long)N * H * W;
-  int lanes = 256 / Cout;
-  long long b = (total + lanes * 16 - 1) / (lanes * 16); long long cap = (long long)svk_num_sms() * 4; if (b > cap) b = cap; if (b < 1) b = 1;
+  int lanes = 256 / (Cout / (dtype == SVK_BF16 ? 8 : 4));
+  long long b = (total + lanes * 16 - 1) / (lanes * 16); long long cap = (long long)svk_num_sms() * 2; if (b > cap) b = cap; if (b < 1) b = 1;
   SVK_DISPATCH_DTYPE(dtype, "stem_conv_wgrad",
     stem_wgrad_kernel<T><<<(int)b, 256, 0, st>>>(x, (const T*)dy, dw, N, H, W, Cout);)
   SVK_LAUNCH_CHECK("stem_conv_wgrad");

@@ -331,7 +331,7 @@ int launch_gather_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP&
     configured = true;
   }
   int grid = p.total_tiles < svk_num_sms() ? p.total_tiles : svk_num_sms();
-  conv_tc_gather_kernel<KC, BN><<<grid, GATHER_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
+  conv_tc_gather_kernel<KC, BN><<<grid, BN <= 64 ? GATHER_THREADS : TC_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
   SVK_LAUNCH_CHECK("conv_tc_gather");
   return 0;
 }

@@ -431,3 +431,108 @@ SVK_API int svk_cast(const void* src, void* dst, long long n, int sd, int dd, vo
   SVK_LAUNCH_CHECK("cast");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------- batched weight packing
+// One launch packs every conv of the network: table rows = {w_off, p_off, Cout, Cin, taps, start} (int64), `start` =
+// cumulative element index.  replaces 35 svk_pack_conv_weight launches per training step.
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS)
+pack_all_kernel(const float* __restrict__ flat, T* __restrict__ wf, T* __restrict__ wd, const long long* __restrict__ table,
+                int nconv, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (k + 1 < nconv && table[(k + 1) * 6 + 5] <= i) ++k;
+    const long long* e = table + k * 6;
+    const long long local = i - e[5];
+    const int Cout = (int)e[2], Cin = (int)e[3], taps = (int)e[4];
+    int t = (int)(local % taps);
+    long long r = local / taps;
+    int ci = (int)(r % Cin);
+    int co = (int)(r / Cin);
+    float v = flat[e[0] + local];
+    wf[e[1] + ((long long)t * Cout + co) * Cin + ci] = from_f<T>(v);
+    wd[e[1] + ((long long)t * Cin + ci) * Cout + co] = from_f<T>(v);
+  }
+}
+SVK_API int svk_pack_conv_weights_batched(const float* flat, void* wf, void* wd, const long long* table, int nconv,
+                                          long long total, int dtype, void* stream) {
+  SVK_REQUIRE(flat && wf && wd && table && nconv > 0 && total > 0, SVK_E_BADARG, "pack_conv_weights_batched: bad args");
+  SVK_DISPATCH_DTYPE(dtype, "pack_conv_weights_batched",
+    pack_all_kernel<T><<<ew_grid(total), EW_THREADS, 0, as_stream(stream)>>>(flat, (T*)wf, (T*)wd, table, nconv, total);)
+  SVK_LAUNCH_CHECK("pack_conv_weights_batched");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- training BN: finalise + apply fused
+// Every thread derives the coefficients of its own V channels from the fp64 sums (cheap), so the 1-block finalise
+// launch disappears; block 0 also publishes scale/shift/mean/rstd (for backward) and updates the running statistics.
+struct BnTrainArgs {
+  const double* stats; const float* gamma; const float* beta; float* rm; float* rv; float* coef; 
+};
+template <int V>
+__device__ inline void bn_train_coefs(const BnTrainArgs& a, long long M, int C, int cstride, int c0, float momentum, float eps,
+                                      bool publish, float (&sc)[V], float (&sh)[V]) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = c0 + i;
+    double mean = a.stats[c] / (double)M;
+    double var = a.stats[C + c] / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    sc[i] = a.gamma[c] * rstd;
+    sh[i] = a.beta[c] - (float)mean * sc[i];
+    if (publish) {
+      a.coef[c] = sc[i]; a.coef[cstride + c] = sh[i]; a.coef[2 * cstride + c] = (float)mean; a.coef[3 * cstride + c] = rstd;
+      if (a.rm) a.rm[c] = (1.f - momentum) * a.rm[c] + momentum * (float)mean;
+      if (a.rv) {
+        double unb = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+        a.rv[c] = (1.f - momentum) * a.rv[c] + momentum * (float)unb;
+      }
+    }
+  }
+}
+template <typename T, int RES /*0 none, 1 plain, 2 second BN*/>
+__global__ void __launch_bounds__(EW_THREADS)
+bn_train_act_kernel(const T* __restrict__ x, BnTrainArgs a, const T* __restrict__ res, BnTrainArgs b, float momentum,
+                    float eps, int relu, T* __restrict__ out, long long nvec, long long M, int C, int cstride) {
+  constexpr int V = Vec<T>::N;
+  const int lanes_c = C / V;
+  long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(i0 % lanes_c) * V;
+  const bool publish = i0 < lanes_c;
+  float sc[V], sh[V], rs[V], rh[V];
+  bn_train_coefs<V>(a, M, C, cstride, c0, momentum, eps, publish, sc, sh);
+  if (RES == 2) bn_train_coefs<V>(b, M, C, cstride, c0, momentum, eps, publish, rs, rh);
+  for (long long iv = i0; iv < nvec; iv += (long long)gridDim.x * blockDim.x) {
+    float v[V], r[V];
+    Vec<T>::load(x + iv * V, v);
+    if (RES) Vec<T>::load(res + iv * V, r);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float y = fmaf(v[i], sc[i], sh[i]);
+      if (RES == 1) y += r[i];
+      if (RES == 2) y += fmaf(r[i], rs[i], rh[i]);
+      v[i] = relu ? fmaxf(y, 0.f) : y;
+    }
+    Vec<T>::store(out + iv * V, v);
+  }
+}
+SVK_API int svk_bn_train_act_fwd(const void* x, const double* stats, const float* gamma, const float* beta, float* rm,
+                                 float* rv, float* coef, const void* res, const double* stats_b, const float* gamma_b,
+                                 const float* beta_b, float* rm_b, float* rv_b, float* coef_b, int cstride, float momentum,
+                                 float eps, int relu, void* out, long long M, int C, int dtype, void* stream) {
+  SVK_REQUIRE(x && stats && gamma && beta && coef && out && cstride >= C, SVK_E_BADARG, "bn_train_act_fwd: bad args");
+  SVK_REQUIRE(!stats_b || (res && gamma_b && beta_b && coef_b), SVK_E_BADARG, "bn_train_act_fwd: second BN args incomplete");
+  if (int e = check_mc("bn_train_act_fwd", M, C, dtype)) return e;
+  BnTrainArgs a{stats, gamma, beta, rm, rv, coef};
+  BnTrainArgs b{stats_b, gamma_b, beta_b, rm_b, rv_b, coef_b};
+  SVK_DISPATCH_DTYPE(dtype, "bn_train_act_fwd",
+    long long nvec = M * C / Vec<T>::N;
+    int g = ew_grid(nvec);
+    cudaStream_t s = as_stream(stream);
+    if (!res) bn_train_act_kernel<T, 0><<<g, EW_THREADS, 0, s>>>((const T*)x, a, nullptr, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);
+    else if (!stats_b) bn_train_act_kernel<T, 1><<<g, EW_THREADS, 0, s>>>((const T*)x, a, (const T*)res, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);
+    else bn_train_act_kernel<T, 2><<<g, EW_THREADS, 0, s>>>((const T*)x, a, (const T*)res, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);)
+  SVK_LAUNCH_CHECK("bn_train_act_fwd");
+  return 0;
+}

@@ -125,17 +125,18 @@ template <int BN>
 __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
                                                 float* scr, const float* coef, int warp, int lane) {
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int group = (warp - 2) >> 2;      // epilogue group g drains accumulator buffer g = every other tile of this CTA
+    const int ngroups = ((int)blockDim.x - 64) >> 7;   // 1 (192 threads) or 2 (320 threads) epilogue warp groups
+    const int group = (warp - 2) >> 2;      // with 2 groups, group g drains accumulator buffer g = every other tile
     float* myscr = scr + (warp - 2) * 32 * 33;
     constexpr int NCH = BN / 32;
     float s1[NCH], s2[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
     int stat_blk = -1;
-    const int acc = group; uint32_t aph = 0;
+    int acc = group; uint32_t aph = 0;
     const int m = q * 32 + lane;            // accumulator row = pixel index inside the tile (loop invariant)
     const int i = m / p.bw, j = m - i * p.bw;
-    for (int tile = blockIdx.x + group * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
+    for (int tile = blockIdx.x + group * gridDim.x; tile < p.total_tiles; tile += ngroups * gridDim.x) {
       const int nblk = tile % p.n_blocks;
       int pt = tile / p.n_blocks;
       const int tw = pt % p.tiles_w; pt /= p.tiles_w;
@@ -226,7 +227,8 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      aph ^= 1u;
+      if (ngroups == 2) aph ^= 1u;
+      else if (++acc == 2) { acc = 0; aph ^= 1u; }
     }
     if (p.stats && stat_blk >= 0) {
 #pragma unroll

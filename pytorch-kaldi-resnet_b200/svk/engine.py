@@ -169,10 +169,15 @@ class SpeakerNetEngine(object):
             self._wf = torch.empty(nconv, dtype=self.act_dtype, device=dev)
             self._wd = torch.empty(nconv, dtype=self.act_dtype, device=dev)
             o = 0
+            poff = {id(p): off for p, off in zip(params, offs)}
+            rows = []
             for c in self.convs:
                 n = c.cout * c.cin * c.R * c.R
                 c.w_fwd, c.w_dgrad = self._wf[o:o + n], self._wd[o:o + n]
+                rows.append([poff[id(c.mod.weight)], o, c.cout, c.cin, c.R * c.R, o])
                 o += n
+            self._pack_table = torch.tensor(rows, dtype=torch.int64, device=dev)
+            self._pack_total = o
             nb = len(self.bns)
             self._nbt = torch.zeros(nb, dtype=torch.long, device=dev)
             for bn in self.bns:
@@ -207,10 +212,9 @@ class SpeakerNetEngine(object):
     def _pack_weights(self):
         if self._packed_version == self._param_version:
             return
-        st = _stream()
-        for c in self.convs:
-            call.svk_pack_conv_weight(c.mod.weight.data_ptr(), c.w_fwd.data_ptr(), c.w_dgrad.data_ptr(), c.cout, c.cin,
-                                      c.R, self.dcode, st)
+        call.svk_pack_conv_weights_batched(self._flat.data_ptr(), self._wf.data_ptr(), self._wd.data_ptr(),
+                                           self._pack_table.data_ptr(), len(self.convs), self._pack_total, self.dcode,
+                                           _stream())
         self._packed_version = self._param_version
 
     # ------------------------------------------------------------------------------------------ workspaces
@@ -269,6 +273,21 @@ class SpeakerNetEngine(object):
                              sh.data_ptr(), mu.data_ptr(), rs.data_ptr(), st)
         return sc, sh
 
+    def _bn_train_act(self, bn, x, out, M, relu, res=None, bn_b=None):
+        """Training BN (statistics already accumulated in self._stats) + activation (+ residual [through bn_b])."""
+        m = bn.mod
+        coef = self._coef[bn.idx]
+        if bn_b is not None:
+            mb = bn_b.mod
+            bargs = (self._stats[bn_b.idx].data_ptr(), mb.weight.data_ptr(), mb.bias.data_ptr(), mb.running_mean.data_ptr(),
+                     mb.running_var.data_ptr(), self._coef[bn_b.idx].data_ptr())
+        else:
+            bargs = (0, 0, 0, 0, 0, 0)
+        call.svk_bn_train_act_fwd(x.data_ptr(), self._stats[bn.idx].data_ptr(), m.weight.data_ptr(), m.bias.data_ptr(),
+                                  m.running_mean.data_ptr(), m.running_var.data_ptr(), coef.data_ptr(), _ptr(res),
+                                  bargs[0], bargs[1], bargs[2], bargs[3], bargs[4], bargs[5], self._cmax, _MOM, _EPS, relu,
+                                  out.data_ptr(), M, bn.C, c_dtype_code(x), _stream())
+
     def _bn_act(self, x, sc, sh, out, M, C, relu, res=None, rsc=None, rsh=None):
         call.svk_bn_act_fwd(x.data_ptr(), sc.data_ptr(), sh.data_ptr(), _ptr(res), _ptr(rsc), _ptr(rsh), relu,
                             out.data_ptr(), M, C, c_dtype_code(x), _stream())
@@ -295,11 +314,10 @@ class SpeakerNetEngine(object):
         a0 = self._buf(ws, "a0", (B, F, T, C0))
         call.svk_stem_conv_fwd(x.data_ptr(), self.stem_conv.weight.data_ptr(), c0.data_ptr(), B, F, T, C0, self.dcode,
                                0, 0, 0, 0, st)
-        sc, sh = self._bn_train(self.stem_bn, c0, M)
-        self._bn_act(c0, sc, sh, a0, M, C0, 1)
+        call.svk_channel_stats(c0.data_ptr(), M, C0, self.dcode, self._stats[self.stem_bn.idx].data_ptr(), st)
+        self._bn_train_act(self.stem_bn, c0, a0, M, 1)
         cur, H, W = a0, F, T
         # ---- residual blocks
-        fused_stats = True          # svk_conv2d_fwd accumulates the BN statistics on both conv paths
         for bi, b in enumerate(self.blocks):
             d1 = self._desc(B, H, W, b.conv1)
             Ho, Wo = d1.Ho, d1.Wo
@@ -310,20 +328,17 @@ class SpeakerNetEngine(object):
             c2 = self._buf(ws, "c2_%d" % bi, (B, Ho, Wo, Co))
             out = self._buf(ws, "o_%d" % bi, (B, Ho, Wo, Co))
             self._conv_fwd(d1, b.conv1, cur, c1, stats=self._stats[b.bn1.idx])
-            sc1, sh1 = self._bn_train(b.bn1, c1, Mo, stats_done=fused_stats)
-            self._bn_act(c1, sc1, sh1, a1, Mo, Co, 1)
+            self._bn_train_act(b.bn1, c1, a1, Mo, 1)
             d2 = self._desc(B, Ho, Wo, b.conv2)
             self._conv_fwd(d2, b.conv2, a1, c2, stats=self._stats[b.bn2.idx])
-            sc2, sh2 = self._bn_train(b.bn2, c2, Mo, stats_done=fused_stats)
             cd = dd = None
             if b.convd is not None:
                 dd = self._desc(B, H, W, b.convd)
                 cd = self._buf(ws, "cd_%d" % bi, (B, Ho, Wo, Co))
                 self._conv_fwd(dd, b.convd, cur, cd, stats=self._stats[b.bnd.idx])
-                scd, shd = self._bn_train(b.bnd, cd, Mo, stats_done=fused_stats)
-                self._bn_act(c2, sc2, sh2, out, Mo, Co, 1, res=cd, rsc=scd, rsh=shd)
+                self._bn_train_act(b.bn2, c2, out, Mo, 1, res=cd, bn_b=b.bnd)
             else:
-                self._bn_act(c2, sc2, sh2, out, Mo, Co, 1, res=cur)
+                self._bn_train_act(b.bn2, c2, out, Mo, 1, res=cur)
             sv["blocks"].append((cur, H, W, c1, a1, c2, cd, out, d1, d2, dd, Ho, Wo))
             cur, H, W = out, Ho, Wo
         # ---- pooling + embedding FC

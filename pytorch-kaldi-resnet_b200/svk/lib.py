@@ -30,6 +30,8 @@ _D = POINTER(ConvDesc)
 # name -> argtypes, exactly as declared in include/svk.h (tests check every symbol is exported)
 SIGNATURES = {
     "svk_pack_conv_weight": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "svk_pack_conv_weights_batched": [_P, _P, _P, _P, _I, _L, _I, _P],
+    "svk_bn_train_act_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P, _L, _I, _I, _P],
     "svk_conv2d_fwd": [_D, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
     "svk_conv2d_dgrad": [_D, _P, _P, _P, _P, _P, _P, _P],
     "svk_conv2d_wgrad": [_D, _P, _P, _P, _P, ctypes.c_size_t, _P],
