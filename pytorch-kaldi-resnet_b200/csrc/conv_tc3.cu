@@ -53,7 +53,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (p.scale) {
-    for (int i = threadIdx.x; i < p.Nout; i += GATHER_THREADS) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
+    for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");

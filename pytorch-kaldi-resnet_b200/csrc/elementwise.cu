@@ -475,10 +475,12 @@ __device__ inline void bn_train_coefs(const BnTrainArgs& a, long long M, int C, 
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = c0 + i;
-    double mean = a.stats[c] / (double)M;
-    double var = a.stats[C + c] / (double)M - mean * mean;
+    // fp64 only where cancellation matters (E[x^2] - E[x]^2); the division / square root run in fp32
+    const double invM = 1.0 / (double)M;           // hoisted by the compiler: loop invariant
+    double mean = a.stats[c] * invM;
+    double var = fma(-mean, mean, a.stats[C + c] * invM);
     if (var < 0.0) var = 0.0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float rstd = 1.0f / sqrtf((float)var + eps);
     sc[i] = a.gamma[c] * rstd;
     sh[i] = a.beta[c] - (float)mean * sc[i];
     if (publish) {
