@@ -1,0 +1,353 @@
+"""GPU parity of the individual kernels, called through the C-ABI (ctypes), against the CPU oracle / torch fp32
+restatements on the same seeded inputs.  Tolerances: fp32 kernels <= 1e-4 relative, bf16 kernels <= 2e-2 relative
+(per-tensor max error / max |reference|), scores <= 1e-3 absolute (BASELINE.json north_star)."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import util
+from oracle import ref_model as O
+from util import call, lib
+
+pytestmark = pytest.mark.gpu
+
+ALL_SHAPES = util.RESNET_SHAPES + util.ODD_SHAPES + util.WIDE_SHAPES
+
+
+# ------------------------------------------------------------------------------------------------ convolutions
+@pytest.mark.parametrize("shape", ALL_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_fp32_validation_path(shape):
+    H, W, ci, co, r, stride = shape
+    x, w, dy = util.make_case(shape, 2, 7, quantize=False)
+    y, stats = util.conv_fwd(x, w, stride, lib.F32, lib.IMPL_SIMT, stats=True)
+    ref = util.ref_conv(x, w, stride)
+    assert util.rel_err(y, ref) <= 1e-4
+    s_ref = torch.cat([ref.double().sum((0, 2, 3)), (ref.double() ** 2).sum((0, 2, 3))])
+    assert util.rel_err(stats, s_ref) <= 1e-5
+    assert util.rel_err(util.conv_dgrad(dy, w, H, W, stride, lib.F32, lib.IMPL_SIMT), util.ref_dgrad(dy, w, H, W, stride)) <= 1e-4
+    assert util.rel_err(util.conv_wgrad(x, dy, r, stride, lib.F32, lib.IMPL_SIMT), util.ref_wgrad(x, dy, r, stride)) <= 1e-4
+
+
+@pytest.mark.parametrize("shape", ALL_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_tcgen05_path(shape):
+    H, W, ci, co, r, stride = shape
+    N = 3
+    x, w, dy = util.make_case(shape, N, 11)            # bf16-exact inputs: the only error is accumulation + output rounding
+    ref = util.ref_conv(x, w, stride)
+    y, stats = util.conv_fwd(x, w, stride, lib.BF16, lib.IMPL_TCGEN05, stats=True)
+    assert not torch.isnan(y).any()
+    assert util.rel_err(y, ref) <= 2e-2
+    s_ref = torch.cat([y.double().sum((0, 2, 3)), (y.double() ** 2).sum((0, 2, 3))])      # statistics of the STORED values
+    assert util.rel_err(stats, s_ref) <= 1e-4
+    if r == 1:   # 1x1/s2 data gradient accumulates into an existing block-input gradient
+        base = util.bf16_round(torch.randn(N, ci, H, W))
+        dx = util.conv_dgrad(dy, w, H, W, stride, lib.BF16, lib.IMPL_TCGEN05, accumulate_into=base)
+        assert util.rel_err(dx, util.ref_dgrad(dy, w, H, W, stride) + base) <= 2e-2
+    else:
+        dx = util.conv_dgrad(dy, w, H, W, stride, lib.BF16, lib.IMPL_TCGEN05)
+        assert util.rel_err(dx, util.ref_dgrad(dy, w, H, W, stride)) <= 2e-2
+    dw = util.conv_wgrad(x, dy, r, stride, lib.BF16, lib.IMPL_TCGEN05)
+    assert not torch.isnan(dw).any()
+    assert util.rel_err(dw, util.ref_wgrad(x, dy, r, stride)) <= 1e-4      # fp32 accumulation and output
+
+
+@pytest.mark.parametrize("impl", [lib.IMPL_SIMT, lib.IMPL_TCGEN05])
+def test_conv_epilogues(impl):
+    """Folded BN scale/shift, residual, ReLU and per-utterance valid widths (extraction path); masked residual (dgrad)."""
+    shape = (10, 50, 128, 128, 3, 1)
+    H, W, ci, co, r, stride = shape
+    N = 3
+    x, w, dy = util.make_case(shape, N, 5)
+    g = torch.Generator().manual_seed(9)
+    scale, shift = torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g)
+    res = util.bf16_round(torch.randn(N, co, H, W, generator=g))
+    valid = torch.tensor([50, 17, 33], dtype=torch.int32)
+    y, _ = util.conv_fwd(x, w, stride, lib.BF16, impl, scale=scale, shift=shift, res_nchw=res, relu=1, valid_wo=valid)
+    ref = F.relu(util.ref_conv(x, w, stride) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res)
+    for n in range(N):
+        ref[n, :, :, int(valid[n]):] = 0
+    assert util.rel_err(y, ref) <= 2e-2
+    assert float(y[1, :, :, 17:].abs().max()) == 0.0
+    mask = util.bf16_round(torch.randn(N, ci, H, W, generator=g))
+    resm = util.bf16_round(torch.randn(N, ci, H, W, generator=g))
+    dx = util.conv_dgrad(dy, w, H, W, stride, lib.BF16, impl, resm_nchw=resm, mask_nchw=mask)
+    assert util.rel_err(dx, util.ref_dgrad(dy, w, H, W, stride) + resm * (mask > 0)) <= 2e-2
+
+
+def test_stem_conv():
+    g = torch.Generator().manual_seed(3)
+    N, H, W, C = 3, 30, 51, 32
+    x = torch.randn(N, H, W, generator=g)
+    w = torch.randn(C, 1, 3, 3, generator=g)
+    ref = F.conv2d(x.unsqueeze(1), w, None, 1, 1)
+    for code, tol in ((lib.F32, 1e-5), (lib.BF16, 2e-2)):
+        y = torch.empty(N, H, W, C, dtype=util.tdtype(code), device="cuda")
+        call.svk_stem_conv_fwd(x.cuda().data_ptr(), w.cuda().data_ptr(), y.data_ptr(), N, H, W, C, code, 0, 0, 0, 0, util.st())
+        assert util.rel_err(util.nchw(y), ref) <= tol
+        dy = util.bf16_round(torch.randn(N, C, H, W, generator=g))
+        dw = torch.empty(C, 9, device="cuda")
+        call.svk_stem_conv_wgrad(x.cuda().data_ptr(), util.nhwc(dy, code).data_ptr(), dw.data_ptr(), N, H, W, C, code, util.st())
+        ref_dw = util.ref_wgrad(x.unsqueeze(1), dy, 3, 1).reshape(C, 9)
+        assert util.rel_err(dw.cpu(), ref_dw) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm
+@pytest.mark.parametrize("code", [lib.F32, lib.BF16])
+@pytest.mark.parametrize("C", [32, 256])
+def test_batchnorm_train_forward_backward(code, C):
+    g = torch.Generator().manual_seed(C)
+    N, H, W = 4, 6, 9
+    M = N * H * W
+    tol = 1e-4 if code == lib.F32 else 2e-2
+    q = (lambda t: t) if code == lib.F32 else util.bf16_round
+    c = q(torch.randn(N, C, H, W, generator=g) * 2 + 0.5)
+    cb = q(torch.randn(N, C, H, W, generator=g))
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    gamma_b, beta_b = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    dout = q(torch.randn(N, C, H, W, generator=g))
+    # oracle: out = relu(bn(c) + bn_b(cb)); gradients w.r.t. c, cb, gamma, beta by autograd
+    cr, cbr = c.clone().requires_grad_(True), cb.clone().requires_grad_(True)
+    gr, br, gbr, bbr = [t.clone().requires_grad_(True) for t in (gamma, beta, gamma_b, beta_b)]
+    rm, rv = torch.zeros(C), torch.ones(C)
+    out_ref = F.relu(F.batch_norm(cr, rm, rv, gr, br, True, 0.1, 1e-5) + F.batch_norm(cbr, None, None, gbr, bbr, True, 0.1, 1e-5))
+    out_ref.backward(dout)
+    dev = lambda t: t.float().cuda()
+    cd, cbd = util.nhwc(c, code), util.nhwc(cb, code)
+    stats = torch.zeros(2, 2 * C, dtype=torch.float64, device="cuda")
+    call.svk_channel_stats(cd.data_ptr(), M, C, code, stats[0].data_ptr(), util.st())
+    call.svk_channel_stats(cbd.data_ptr(), M, C, code, stats[1].data_ptr(), util.st())
+    coef = torch.zeros(2, 4, C, device="cuda")
+    rmd, rvd = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    out = torch.empty_like(cd)
+    gd, bd, gbd, bbd = dev(gamma), dev(beta), dev(gamma_b), dev(beta_b)
+    call.svk_bn_train_act_fwd(cd.data_ptr(), stats[0].data_ptr(), gd.data_ptr(), bd.data_ptr(), rmd.data_ptr(), rvd.data_ptr(),
+                              coef[0].data_ptr(), cbd.data_ptr(), stats[1].data_ptr(), gbd.data_ptr(), bbd.data_ptr(), 0, 0,
+                              coef[1].data_ptr(), C, 0.1, 1e-5, 1, out.data_ptr(), M, C, code, util.st())
+    assert util.rel_err(util.nchw(out), out_ref.detach()) <= tol
+    assert util.rel_err(rmd.cpu(), rm) <= 1e-5 and util.rel_err(rvd.cpu(), rv) <= 1e-5      # running stats (unbiased var)
+    # the separate finalise kernel publishes the same coefficients
+    coef2 = torch.zeros(4, C, device="cuda")
+    call.svk_bn_finalize(stats[0].data_ptr(), M, C, gd.data_ptr(), bd.data_ptr(), 0, 0, 0.1, 1e-5, coef2[0].data_ptr(),
+                         coef2[1].data_ptr(), coef2[2].data_ptr(), coef2[3].data_ptr(), util.st())
+    assert util.rel_err(coef2.cpu(), coef[0].cpu()) <= 1e-5
+    # backward
+    sums = torch.zeros(3 * C, dtype=torch.float64, device="cuda")
+    dd = util.nhwc(dout, code)
+    call.svk_bn_bwd_reduce(dd.data_ptr(), out.data_ptr(), cd.data_ptr(), coef[0][2].data_ptr(), coef[0][3].data_ptr(),
+                           cbd.data_ptr(), coef[1][2].data_ptr(), coef[1][3].data_ptr(), sums.data_ptr(), M, C, code, util.st())
+    dc, dcb = torch.empty_like(cd), torch.empty_like(cd)
+    grads = torch.zeros(4, C, device="cuda")
+    call.svk_bn_bwd_apply(dd.data_ptr(), out.data_ptr(), cd.data_ptr(), coef[0][2].data_ptr(), coef[0][3].data_ptr(),
+                          gd.data_ptr(), dc.data_ptr(), cbd.data_ptr(), coef[1][2].data_ptr(), coef[1][3].data_ptr(),
+                          gbd.data_ptr(), dcb.data_ptr(), sums.data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(),
+                          grads[2].data_ptr(), grads[3].data_ptr(), M, C, code, util.st())
+    # in bf16 the CUDA mask comes from the rounded `out`; flips of |v| < 2^-9 are excluded by the norm-wise bound
+    assert float((util.nchw(dc) - cr.grad).norm() / cr.grad.norm()) <= tol
+    assert float((util.nchw(dcb) - cbr.grad).norm() / cbr.grad.norm()) <= tol
+    for got, ref in zip(grads.cpu(), (gr.grad, br.grad, gbr.grad, bbr.grad)):
+        assert util.rel_err(got, ref) <= tol
+
+
+# ------------------------------------------------------------------------------------------------ pooling, FC, head, loss
+@pytest.mark.parametrize("mode", [0, 1])
+def test_stats_pooling(mode):
+    g = torch.Generator().manual_seed(2)
+    N, C, H, W = 3, 256, 5, 13
+    x = F.relu(torch.randn(N, C, H, W, generator=g))
+    x[0, 3, 2, :] = 0                                        # an all-zero row: sqrt(mean)=0, gradient defined as 0
+    pooling = "mean+std" if mode else "mean"
+    xr = x.clone().requires_grad_(True)
+    ref = torch.flatten(O.stats_pooling(xr, pooling), 1, -1)
+    dout = torch.randn(ref.shape, generator=g)
+    xd = util.nhwc(x, lib.F32)
+    out = torch.empty(N, ref.shape[1], device="cuda")
+    call.svk_statspool_fwd(xd.data_ptr(), out.data_ptr(), N, H, W, C, mode, 0, lib.F32, util.st())
+    assert util.rel_err(out.cpu(), ref.detach()) <= 1e-5
+    dx = torch.empty_like(xd)
+    call.svk_statspool_bwd(xd.data_ptr(), dout.cuda().data_ptr(), dx.data_ptr(), N, H, W, C, mode, lib.F32, util.st())
+    (ref * dout).sum().backward()
+    gref = torch.nan_to_num(xr.grad, nan=0.0, posinf=0.0, neginf=0.0) * (x > 0)      # what survives the ReLU mask upstream
+    assert util.rel_err(util.nchw(dx) * (x > 0), gref) <= 1e-5
+    # per-utterance valid widths
+    lens = torch.tensor([13, 7, 10], dtype=torch.int32)
+    call.svk_statspool_fwd(xd.data_ptr(), out.data_ptr(), N, H, W, C, mode, lens.cuda().data_ptr(), lib.F32, util.st())
+    for n in range(N):
+        r = torch.flatten(O.stats_pooling(x[n:n + 1, :, :, :int(lens[n])], pooling), 1, -1)
+        assert util.rel_err(out[n:n + 1].cpu(), r) <= 1e-5
+
+
+def test_sgemm_all_layouts():
+    g = torch.Generator().manual_seed(4)
+    M, N, K = 70, 130, 45
+    A, B, bias = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g), torch.randn(N, generator=g)
+    ref = A @ B + bias
+    for at in (False, True):
+        for bt in (False, True):
+            a = (A.t().contiguous() if at else A).cuda()
+            b = (B.t().contiguous() if bt else B).cuda()
+            c = torch.empty(M, N, device="cuda")
+            call.svk_sgemm(a.data_ptr(), 1 if at else K, M if at else 1, b.data_ptr(), 1 if bt else N, K if bt else 1,
+                           c.data_ptr(), N, M, N, K, 1.0, 0.0, bias.cuda().data_ptr(), util.st())
+            assert util.rel_err(c.cpu(), ref) <= 1e-5
+
+
+def test_aam_head_and_cross_entropy():
+    from svk.loss import CrossEntropyLoss, accuracy
+    g = torch.Generator().manual_seed(6)
+    B, E, C, m, s = 16, 256, 301, 0.2, 30.0
+    x, w = torch.randn(B, E, generator=g), torch.randn(C, E, generator=g) * 0.1
+    y = torch.randint(0, C, (B,), generator=g)
+    w[y[0]] = x[0] * 3                                       # one very confident target: exercises cos > th and sine ~ 0
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    logits_ref = O.aam_logits(xr, wr, y, m, s)
+    loss_ref = O.cross_entropy(logits_ref, y)
+    loss_ref.backward()
+    cos_m, sin_m, th, mm = O.aam_constants(m)
+    st = util.st()
+    xd, wd, yd = x.cuda(), w.cuda(), y.cuda()
+    xh, wh = torch.empty_like(xd), torch.empty_like(wd)
+    xinv, winv = torch.empty(B, device="cuda"), torch.empty(C, device="cuda")
+    call.svk_l2norm_rows_fwd(xd.data_ptr(), xh.data_ptr(), xinv.data_ptr(), B, E, 1e-12, st)
+    call.svk_l2norm_rows_fwd(wd.data_ptr(), wh.data_ptr(), winv.data_ptr(), C, E, 1e-12, st)
+    logits = torch.empty(B, C, device="cuda")
+    call.svk_sgemm(xh.data_ptr(), E, 1, wh.data_ptr(), 1, E, logits.data_ptr(), C, B, C, E, 1.0, 0.0, 0, st)
+    cos_t = torch.empty(B, device="cuda")
+    call.svk_aam_margin_fwd(logits.data_ptr(), yd.data_ptr(), cos_t.data_ptr(), B, C, cos_m, sin_m, th, mm, s, st)
+    assert util.rel_err(logits.cpu(), logits_ref.detach()) <= 1e-5
+    lg = logits.clone().requires_grad_(True)
+    loss = CrossEntropyLoss()(lg, yd)
+    assert abs(float(loss) - float(loss_ref.detach())) <= 1e-5
+    loss.backward()
+    a_ref = O.accuracy(logits_ref.detach(), y, (1, 5))
+    a_got = accuracy(logits, yd, (1, 5))
+    assert [float(a_got[0]), float(a_got[1])] == [float(a_ref[0]), float(a_ref[1])]
+    d = lg.grad.clone()
+    call.svk_aam_margin_bwd(d.data_ptr(), yd.data_ptr(), cos_t.data_ptr(), B, C, cos_m, sin_m, th, s, st)
+    dxh, dwh = torch.empty(B, E, device="cuda"), torch.empty(C, E, device="cuda")
+    call.svk_sgemm(d.data_ptr(), C, 1, wh.data_ptr(), E, 1, dxh.data_ptr(), E, B, E, C, 1.0, 0.0, 0, st)
+    call.svk_sgemm(d.data_ptr(), 1, C, xh.data_ptr(), E, 1, dwh.data_ptr(), E, C, E, B, 1.0, 0.0, 0, st)
+    dx, dw = torch.empty_like(xd), torch.empty_like(wd)
+    call.svk_l2norm_rows_bwd(dxh.data_ptr(), xh.data_ptr(), xinv.data_ptr(), dx.data_ptr(), B, E, st)
+    call.svk_l2norm_rows_bwd(dwh.data_ptr(), wh.data_ptr(), winv.data_ptr(), dw.data_ptr(), C, E, st)
+    assert util.rel_err(dx.cpu(), xr.grad) <= 1e-4
+    assert util.rel_err(dw.cpu(), wr.grad) <= 1e-4
+
+
+def test_sgd_matches_torch_sgd_over_three_steps():
+    from svk.optim import SGD
+    g = torch.Generator().manual_seed(8)
+    p0 = [torch.randn(37, 5, generator=g), torch.randn(11, generator=g)]
+    grads = [[torch.randn(37, 5, generator=g), torch.randn(11, generator=g)] for _ in range(3)]
+    ref = [t.clone().requires_grad_(True) for t in p0]
+    mine = [t.clone().cuda().requires_grad_(True) for t in p0]
+    o_ref = torch.optim.SGD(ref, 0.1, momentum=0.9, weight_decay=5e-4)
+    o_mine = SGD(mine, 0.1, momentum=0.9, weight_decay=5e-4)
+    for step in range(3):
+        for t, m_, gr in zip(ref, mine, grads[step]):
+            t.grad = gr.clone()
+            m_.grad = gr.clone().cuda()
+        o_ref.step()
+        o_mine.step()
+    for t, m_ in zip(ref, mine):
+        assert util.rel_err(m_.detach().cpu(), t.detach()) <= 1e-6
+    sd = o_mine.state_dict()                                  # torch's state-dict layout: loads into torch.optim.SGD
+    o_ref.load_state_dict({"state": {k: {"momentum_buffer": v["momentum_buffer"].cpu()} for k, v in sd["state"].items()},
+                           "param_groups": sd["param_groups"]})
+
+
+# ------------------------------------------------------------------------------------------------ scoring
+def test_scoring_kernels_match_reference_scripts():
+    from svk import scoring
+    fx = np.load(os.path.join(util.ROOT, "tests", "golden", "scoring.npz"))
+    emb64 = np.array([[float(t) for t in map(str, v)] for v in fx["emb"]], dtype=np.float64)
+    coh64 = np.array([[float(t) for t in map(str, v)] for v in fx["coh"]], dtype=np.float64)
+    mean64 = np.array([float(t) for t in map(str, fx["mean"])], dtype=np.float64)
+    e32 = (emb64 - mean64).astype(np.float32)
+    c32 = (coh64 - mean64).astype(np.float32)
+    s = scoring.cosine_scores(e32, e32, None, fx["ie"], fx["it"]).cpu().numpy()
+    assert np.abs(s - fx["scores"]).max() <= 1e-6            # north-star bound: 1e-3 absolute
+    m, sd = scoring.cohort_topk_meanstd(e32, c32, topk=300, block_rows=16)
+    assert np.abs(m.cpu().numpy() - fx["topk_mean"]).max() <= 1e-6
+    assert np.abs(sd.cpu().numpy() - fx["topk_std"]).max() <= 1e-6
+    sn = scoring.snorm_apply(fx["scores"], fx["ie"], fx["it"], fx["topk_mean"], fx["topk_std"], fx["topk_mean"],
+                             fx["topk_std"]).cpu().numpy()
+    assert np.abs(sn - fx["snorm"]).max() <= 1e-4
+    # edge cases: ties at the k-th value, k == cohort size, empty trial list
+    ties = torch.zeros(2, 400)
+    ties[0, :250] = 1.0
+    ties[1] = torch.arange(400).float()
+    mean = torch.empty(2, device="cuda")
+    std = torch.empty(2, device="cuda")
+    call.svk_topk_meanstd(ties.cuda().data_ptr(), 2, 400, 300, mean.data_ptr(), std.data_ptr(), util.st())
+    ref0 = torch.cat([torch.ones(250), torch.zeros(50)])
+    assert abs(float(mean[0]) - float(ref0.mean())) <= 1e-6 and abs(float(std[0]) - float(ref0.std())) <= 1e-6
+    assert abs(float(mean[1]) - 249.5) <= 1e-3 and abs(float(std[1]) - float(torch.arange(100, 400).float().std())) <= 1e-3
+    assert scoring.cosine_scores(e32, e32, None, np.zeros(0, np.int32), np.zeros(0, np.int32)).numel() == 0
+
+
+def test_scoring_scripts_end_to_end_on_reference_files():
+    """The CLI drop-ins read the files the reference's own scripts read and reproduce their output files."""
+    fx = np.load(os.path.join(util.ROOT, "tests", "golden", "scoring.npz"))
+    scripts = os.path.join(util.PKG, "scripts")
+    with tempfile.TemporaryDirectory() as d:
+        for k in ("emb.iv", "coh.iv", "mean.vec", "trials"):
+            open(os.path.join(d, k), "w").write(str(fx["file/" + k]))
+        run = lambda *a: subprocess.run([sys.executable] + list(a), check=True, capture_output=True, cwd=d)
+        run(os.path.join(scripts, "cosine_score.py"), "--mean", "mean.vec", "--enroll", "emb.iv", "--test", "emb.iv",
+            "--trials", "trials", "--score-file", "scores")
+        run(os.path.join(scripts, "compute_topk_mean_std.py"), "--mean", "mean.vec", "--ark-file", "emb.iv", "--cohort-file",
+            "coh.iv", "--mean-std-file", "topk")
+        run(os.path.join(scripts, "adaptive_snorm.py"), "--enroll", "topk", "--test", "topk", "--score-in", "scores",
+            "--score-out", "snorm")
+        ref_lines = str(fx["file/scores"]).splitlines()
+        got_lines = open(os.path.join(d, "scores")).read().splitlines()
+        assert [l.split()[:2] for l in got_lines] == [l.split()[:2] for l in ref_lines]
+        assert np.abs(np.array([float(l.split()[2]) for l in got_lines]) - fx["scores"]).max() <= 1e-6
+        got_sn = np.array([float(l.split()[2]) for l in open(os.path.join(d, "snorm"))])
+        assert np.abs(got_sn - fx["snorm"]).max() <= 1e-3
+        topk = [l.split() for l in open(os.path.join(d, "topk"))]
+        assert [t[0] for t in topk] == list(fx["utts"])
+        assert np.abs(np.array([float(t[1]) for t in topk]) - fx["topk_mean"]).max() <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ extraction CLI
+def test_decode_script_matches_batch1_oracle():
+    """decode.py on a synthetic ark of variable-length utterances: text vectors in the reference's format, equal (cosine
+    >= 0.999, bf16) to the oracle's batch-1 eval embedding of every utterance."""
+    import contextlib
+    import io
+    import kaldi_io
+    from model import NeuralSpeakerModel
+    rs = np.random.RandomState(5)
+    lengths = [40, 41, 57, 57, 96, 133]
+    mats = {"utt%02d" % i: rs.randn(t, 40).astype(np.float32) for i, t in enumerate(lengths)}
+    torch.manual_seed(21)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = NeuralSpeakerModel(spk_num=12, feat_dim=40, pooling="mean+std", loss="AAM")
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    with tempfile.TemporaryDirectory() as d:
+        ark, scp = os.path.join(d, "feats.ark"), os.path.join(d, "feats.scp")
+        with open(ark, "wb") as f, open(scp, "w") as s:
+            for key, mat in mats.items():
+                f.write((key + " ").encode())
+                s.write("%s %s:%d\n" % (key, ark, f.tell()))
+                kaldi_io.write_mat(f, mat)
+        torch.save({"epoch": 1, "arch": "resnet34", "state_dict": {"module." + k: v for k, v in sd.items()},
+                    "best_acc1": 0.0, "optimizer": {}}, os.path.join(d, "ckpt.pth.tar"))
+        subprocess.run([sys.executable, os.path.join(util.PKG, "scripts", "decode.py"), "--spk_num", "12", "--input-dim", "40",
+                        "--pooling", "mean+std", "--model-path", os.path.join(d, "ckpt.pth.tar"), "--decode-scp", scp,
+                        "--out-path", os.path.join(d, "emb"), "--gpu", "0", "--max-batch-frames", "200"],
+                       check=True, capture_output=True)
+        got = dict(kaldi_io.read_vec_flt_ark(os.path.join(d, "emb", "0")))
+    assert sorted(got) == sorted(mats)
+    for key, mat in mats.items():
+        with torch.no_grad():
+            ref = O.embed(sd, torch.from_numpy(mat.T.copy()).unsqueeze(0), "mean+std", train=False)[0]
+        cos = float(F.cosine_similarity(torch.from_numpy(got[key]).float(), ref, dim=0))
+        assert cos >= 0.999, (key, cos)

@@ -164,7 +164,7 @@ def test_train_step_fp32_matches_reference(case):
     loss2 = crit(m(x, y), y)
     loss2.backward()
     opt.step()
-    assert abs(float(loss2) - float(fx["loss2"])) <= 2e-3 * max(1.0, abs(float(fx["loss2"])))
+    assert abs(float(loss2) - float(fx["loss2"])) <= (2e-3 if strict else 3e-2) * max(1.0, abs(float(fx["loss2"])))
 
 
 @pytest.mark.parametrize("impl", ["tcgen05", "simt"])
