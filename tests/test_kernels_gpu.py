@@ -86,13 +86,15 @@ def test_stem_conv():
     x = torch.randn(N, H, W, generator=g)
     w = torch.randn(C, 1, 3, 3, generator=g)
     ref = F.conv2d(x.unsqueeze(1), w, None, 1, 1)
+    xd, wd = x.cuda(), w.cuda()                      # keep the device copies alive across the asynchronous launches
     for code, tol in ((lib.F32, 1e-5), (lib.BF16, 2e-2)):
         y = torch.empty(N, H, W, C, dtype=util.tdtype(code), device="cuda")
-        call.svk_stem_conv_fwd(x.cuda().data_ptr(), w.cuda().data_ptr(), y.data_ptr(), N, H, W, C, code, 0, 0, 0, 0, util.st())
+        call.svk_stem_conv_fwd(xd.data_ptr(), wd.data_ptr(), y.data_ptr(), N, H, W, C, code, 0, 0, 0, 0, util.st())
         assert util.rel_err(util.nchw(y), ref) <= tol
         dy = util.bf16_round(torch.randn(N, C, H, W, generator=g))
+        dyd = util.nhwc(dy, code)
         dw = torch.empty(C, 9, device="cuda")
-        call.svk_stem_conv_wgrad(x.cuda().data_ptr(), util.nhwc(dy, code).data_ptr(), dw.data_ptr(), N, H, W, C, code, util.st())
+        call.svk_stem_conv_wgrad(xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), N, H, W, C, code, util.st())
         ref_dw = util.ref_wgrad(x.unsqueeze(1), dy, 3, 1).reshape(C, 9)
         assert util.rel_err(dw.cpu(), ref_dw) <= 1e-4
 
@@ -170,13 +172,15 @@ def test_stats_pooling(mode):
     call.svk_statspool_fwd(xd.data_ptr(), out.data_ptr(), N, H, W, C, mode, 0, lib.F32, util.st())
     assert util.rel_err(out.cpu(), ref.detach()) <= 1e-5
     dx = torch.empty_like(xd)
-    call.svk_statspool_bwd(xd.data_ptr(), dout.cuda().data_ptr(), dx.data_ptr(), N, H, W, C, mode, lib.F32, util.st())
+    doutd = dout.cuda()
+    call.svk_statspool_bwd(xd.data_ptr(), doutd.data_ptr(), dx.data_ptr(), N, H, W, C, mode, lib.F32, util.st())
     (ref * dout).sum().backward()
     gref = torch.nan_to_num(xr.grad, nan=0.0, posinf=0.0, neginf=0.0) * (x > 0)      # what survives the ReLU mask upstream
     assert util.rel_err(util.nchw(dx) * (x > 0), gref) <= 1e-5
     # per-utterance valid widths
     lens = torch.tensor([13, 7, 10], dtype=torch.int32)
-    call.svk_statspool_fwd(xd.data_ptr(), out.data_ptr(), N, H, W, C, mode, lens.cuda().data_ptr(), lib.F32, util.st())
+    lensd = lens.cuda()
+    call.svk_statspool_fwd(xd.data_ptr(), out.data_ptr(), N, H, W, C, mode, lensd.data_ptr(), lib.F32, util.st())
     for n in range(N):
         r = torch.flatten(O.stats_pooling(x[n:n + 1, :, :, :int(lens[n])], pooling), 1, -1)
         assert util.rel_err(out[n:n + 1].cpu(), r) <= 1e-5
@@ -192,8 +196,9 @@ def test_sgemm_all_layouts():
             a = (A.t().contiguous() if at else A).cuda()
             b = (B.t().contiguous() if bt else B).cuda()
             c = torch.empty(M, N, device="cuda")
+            biasd = bias.cuda()
             call.svk_sgemm(a.data_ptr(), 1 if at else K, M if at else 1, b.data_ptr(), 1 if bt else N, K if bt else 1,
-                           c.data_ptr(), N, M, N, K, 1.0, 0.0, bias.cuda().data_ptr(), util.st())
+                           c.data_ptr(), N, M, N, K, 1.0, 0.0, biasd.data_ptr(), util.st())
             assert util.rel_err(c.cpu(), ref) <= 1e-5
 
 
@@ -284,7 +289,8 @@ def test_scoring_kernels_match_reference_scripts():
     ties[1] = torch.arange(400).float()
     mean = torch.empty(2, device="cuda")
     std = torch.empty(2, device="cuda")
-    call.svk_topk_meanstd(ties.cuda().data_ptr(), 2, 400, 300, mean.data_ptr(), std.data_ptr(), util.st())
+    tiesd = ties.cuda()
+    call.svk_topk_meanstd(tiesd.data_ptr(), 2, 400, 300, mean.data_ptr(), std.data_ptr(), util.st())
     ref0 = torch.cat([torch.ones(250), torch.zeros(50)])
     assert abs(float(mean[0]) - float(ref0.mean())) <= 1e-6 and abs(float(std[0]) - float(ref0.std())) <= 1e-6
     assert abs(float(mean[1]) - 249.5) <= 1e-3 and abs(float(std[1]) - float(torch.arange(100, 400).float().std())) <= 1e-3
