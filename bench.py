@@ -229,11 +229,14 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks}
 
+    # ---- per-kernel device times of one step, measured live with CUDA events on the launching stream.  EVERY rank runs
+    # this step (it contains the gradient all-reduce); only rank 0 records and reports.
     if rank == 0:
-        # ---- per-kernel device times of one step, measured live with CUDA events on the launching stream
         lib.profile_begin()
-        step(x_dev, y_dev)
-        prof = lib.profile_end()
+    step(x_dev, y_dev)
+    prof = lib.profile_end() if rank == 0 else None
+    barrier()
+    if rank == 0:
         agg = {}
         for name, tag, ms in prof:
             key = name
@@ -273,12 +276,72 @@ def run_ours(args):
         if wg:
             line["roofline_wgrad"] = {"bound": "tensor", "achieved": wg[2] / (wg[0] / 1e3) / 1e12, "peak": tf, "unit": "TFLOP/s",
                                       "frac": wg[2] / (wg[0] / 1e3) / 1e12 / tf, "share_of_step": wg[0] / total_prof}
+        if world == 1 and not args.no_extras:
+            try:
+                line["extra"] = extras(net, dev)
+            except Exception as ex:          # secondary numbers must never break the headline line
+                line["extra"] = {"error": str(ex)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference(3, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def extras(net, dev):
+    """Secondary numbers of BASELINE.json config 2 on one GPU (not part of `value`): whole-utterance extraction through
+    scripts/decode.py::extract on a 512-utterance sample of the 4,708-utterance VoxCeleb1-O-shaped set
+    (T = clip(round(exp(N(ln 650, 0.55^2))), 200, 6000), RandomState(1234); host -> device copies included), and cosine
+    scoring of 37,720 trial pairs."""
+    import numpy as np
+    import torch
+    import decode
+    from svk import scoring
+    rs = np.random.RandomState(1234)
+    T = np.clip(np.round(np.exp(rs.normal(np.log(650.0), 0.55, 4708))), 200, 6000).astype(int)[:512]
+
+    class Mem(object):
+        seq_len = -1
+        utts = ["utt%05d" % i for i in range(len(T))]
+        mats = [rs.randn(FEAT, int(t)).astype(np.float32) for t in T]
+
+        def __len__(self):
+            return len(self.mats)
+
+        def num_frames(self, i):
+            return self.mats[i].shape[1]
+
+        def __getitem__(self, i):
+            return self.mats[i], [self.utts[i]]
+    ds = Mem()
+    net.eval()
+    out = {}
+    decode.extract(net, ds, list(range(32)), dev, 65536, lambda u, v: None)            # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    decode.extract(net, ds, list(range(len(ds))), dev, 65536, lambda u, v: out.__setitem__(u, v))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    emb = np.stack([out[u] for u in ds.utts]).astype(np.float32)
+    big = np.concatenate([emb] * 10)[:4708]
+    ie = rs.randint(0, 4708, 37720).astype(np.int32)
+    it = rs.randint(0, 4708, 37720).astype(np.int32)
+    E = torch.from_numpy(big).to(dev)
+    mean = E.mean(0)
+    ied, itd = torch.from_numpy(ie).to(dev), torch.from_numpy(it).to(dev)
+    scoring.cosine_scores(E, E, mean, ied, itd, device=dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        scoring.cosine_scores(E, E, mean, ied, itd, device=dev)
+    e1.record()
+    torch.cuda.synchronize()
+    net.train()
+    return {"extract_utts_per_sec": len(ds) / dt, "extract_frames_per_sec": float(T.sum()) / dt,
+            "extract_sample": "512 of the 4708 cfg2 utterances (%d frames), length-sorted padded batches, H2D included" % int(T.sum()),
+            "score_trials_per_sec": 37720 / (e0.elapsed_time(e1) / 10 / 1e3), "score_sample": "37,720 trials, device-resident"}
 
 
 def main():
@@ -289,6 +352,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="chunks per GPU per step (256 = BASELINE.json config 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary extraction / scoring numbers")
     ap.add_argument("--profile-out", default="", help="write the per-(kernel, shape) CUDA-event times of one step here")
     args = ap.parse_args()
     if args.impl == "reference":

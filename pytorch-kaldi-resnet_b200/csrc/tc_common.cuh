@@ -3,6 +3,7 @@
 #pragma once
 #include "svk_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 typedef __nv_bfloat16 bf16;
 
@@ -260,6 +261,11 @@ inline int make_nhwc_map(CUtensorMap* m, const void* ptr, int N, int H, int W, i
   SVK_REQUIRE(enc, SVK_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  {   // timing experiment only (wrong results): SVK_DEBUG_NO_ESTRIDE=1 replaces strided boxes by dense ones
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("SVK_DEBUG_NO_ESTRIDE"); dbg = (e && e[0] == '1') ? 1 : 0; }
+    if (dbg) es = 1;
+  }
   cuuint32_t box[4] = {(cuuint32_t)ck, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   SVK_REQUIRE(box[1] <= 256 && box[2] <= 256, SVK_E_UNSUPPORTED, "conv_tc: TMA box %ux%u too large", box[1], box[2]);
