@@ -451,18 +451,21 @@ namespace {
 
 // Pixel tile for wgrad: P = bh*bw a multiple of 16 (UMMA K), <= 128 rows; rshift additionally needs bw % 8 == 0 so that a
 // shift by r*bw rows is a whole number of swizzle atoms.  Cost = smem rows fetched per pixel of work.
-void pick_wgrad_tile(int Ho, int Wo, int es, int rshift, int* bh_out, int* bw_out) {
+void pick_wgrad_tile(int Ho, int Wo, int es, int rshift, int taps_cta, int row_bytes_total, int* bh_out, int* bw_out) {
+  // cost of one pixel tile = fixed pipeline latency + max(tensor cycles, smem-ingest cycles); total = tiles * cost.
+  // (Without the fixed term every exact-fit tile ties and a 16-pixel tile wins: 7,600 cycles per tile of pure overhead.)
   double best = 1e30; int bbh = 0, bbw = 0;
   const int max_bw = 256 / es;
   for (int bw = rshift ? 8 : 1; bw <= max_bw && bw <= 128; bw += rshift ? 8 : 1) {
-    for (int bh = 1; bh * bw <= 128 && bh <= Ho + 1; ++bh) {
-      if ((bh * bw) % 16 != 0) continue;
-      if (rshift && (bh + 2) > 256) continue;
+    for (int bh = 1; bh * bw <= 128 && bh <= Ho + 1 && (bh + 2) * es <= 256; ++bh) {
+      const int P = bh * bw;
+      if (P % 16 != 0) continue;
       int th = (Ho + bh - 1) / bh, tw = (Wo + bw - 1) / bw;
-      double rows = (double)th * tw * (bh * bw + (rshift ? (bh + 2) * bw : 3.0 * bh * bw));   // dy + x rows per s
-      double mma = (double)th * tw * bh * bw;
-      double cost = rows + 2.0 * mma;
-      if (cost < best) { best = cost; bbh = bh; bbw = bw; }
+      double x_rows = rshift ? (double)(bh + 2) * bw : (double)taps_cta * P;
+      double ingest = (P + x_rows) * row_bytes_total / 48.0;
+      double mma = (double)taps_cta * (P / 16) * 64.0;
+      double cost = (double)th * tw * (600.0 + (mma > ingest ? mma : ingest));
+      if (cost < best - 1e-9) { best = cost; bbh = bh; bbw = bw; }
     }
   }
   *bh_out = bbh; *bw_out = bbw;
@@ -485,7 +488,7 @@ int plan_wgrad(const svk_conv_desc* d, WgradP* pp, int* ck_out, size_t* smem_out
     p.n_tap_grp = (p.ntaps + max_taps - 1) / max_taps;
     p.taps_per_grp = (p.ntaps + p.n_tap_grp - 1) / p.n_tap_grp;
   }
-  pick_wgrad_tile(d->Ho, d->Wo, d->stride, p.rshift, &p.bh, &p.bw);
+  pick_wgrad_tile(d->Ho, d->Wo, d->stride, p.rshift, p.taps_per_grp, (p.cin_blk > 128 ? 128 : p.cin_blk) * 2 + 64, &p.bh, &p.bw);
   SVK_REQUIRE(p.bh > 0, SVK_E_UNSUPPORTED, "conv2d_wgrad(tc): no pixel tile for %dx%d", d->Ho, d->Wo);
   p.P = p.bh * p.bw;
   p.xrows = p.rshift ? (p.bh + 2) * p.bw : p.P;
