@@ -256,3 +256,48 @@ def test_kat_seed0_full_size():
     e = m.predict(x[:1]).float().cpu()
     cos = float(F.cosine_similarity(e, torch.from_numpy(fx["embed"]), dim=1))
     assert cos >= 0.999, cos
+
+
+def test_wide_variant_train_step_vs_live_oracle():
+    """BASELINE.json config 4 (2x channels): the reference has no width knob, so the oracle composes the same
+    block functions over the wide state-dict; fp32 validation mode, one training step."""
+    from model import NeuralSpeakerModel
+    from svk.loss import CrossEntropyLoss
+    torch.manual_seed(17)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = NeuralSpeakerModel(spk_num=23, feat_dim=40, pooling="mean+std", loss="AAM", precision="fp32",
+                               widths=(64, 128, 256, 512))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    g = torch.Generator().manual_seed(3)
+    x, y = torch.randn(3, 40, 44, generator=g), torch.randint(0, 23, (3,), generator=g)
+    names = O.param_names(sd)
+    for n_ in names:
+        sd[n_].requires_grad_(True)
+    ref = O.model_forward(sd, x, y, "mean+std", "AAM", 0.2, 30, True, {})
+    lref = O.cross_entropy(ref, y)
+    lref.backward()
+    m.train()
+    out = m(x.cuda(), y.cuda())
+    loss = CrossEntropyLoss()(out, y.cuda())
+    loss.backward()
+    assert util.rel_err(out.detach().cpu(), ref.detach()) <= 1e-4
+    assert abs(float(loss) - float(lref.detach())) <= 1e-5 * float(lref.detach())
+    worst = 0.0
+    for nm, p in m.named_parameters():
+        gref = sd[nm].grad
+        worst = max(worst, float((p.grad.cpu() - gref).norm() / gref.norm()))
+    assert worst <= 2e-3, "norm-wise gradient error %.2e" % worst      # norm-wise: robust to ReLU-tie flips (DESIGN.md §6)
+    # bf16 tcgen05 path of the same wide model: loss within 2e-2, eval embeddings cosine >= 0.999
+    torch.manual_seed(17)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mb = NeuralSpeakerModel(spk_num=23, feat_dim=40, pooling="mean+std", loss="AAM", widths=(64, 128, 256, 512)).cuda()
+    mb.eval()
+    e = mb.predict(x.cuda()).float().cpu()
+    with torch.no_grad():
+        eref = O.embed({k: v.detach() for k, v in sd.items()}, x, "mean+std", train=False)
+    assert float(F.cosine_similarity(e, eref, dim=1).min()) >= 0.999
+    mb.train()
+    lb = CrossEntropyLoss()(mb(x.cuda(), y.cuda()), y.cuda())
+    lb.backward()
+    assert abs(float(lb) - float(lref.detach())) <= 2e-2 * float(lref.detach())
