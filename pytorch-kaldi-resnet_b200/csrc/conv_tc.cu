@@ -73,7 +73,8 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {   // the WHOLE warp runs this loop (warp-uniform control flow lets ptxas keep descriptors and coordinates in
+        // uniform registers); the issuing wrappers elect one lane
       int stage = 0; uint32_t ph = 0;
       const uint32_t a_bytes = (uint32_t)(p.bh * p.bw) * Cfg::ROWB;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -87,9 +88,10 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
             const uint32_t sa = stage0 + stage * Cfg::STAGE;
-            mbar_expect_tx(bar_full + 8 * stage, a_bytes + Cfg::B_BYTES);
-            tma_load_4d(sa, &tmA, bar_full + 8 * stage, kc * KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n);
-            tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full + 8 * stage, kc * KC, p.tap_w[t] * p.Nout + nblk * BN);
+            mbar_expect_tx(bar_full + 8 * stage, ((p.dbg & 2) ? 0u : a_bytes) + ((p.dbg & 1) ? 0u : (uint32_t)Cfg::B_BYTES));
+            if (!(p.dbg & 2)) tma_load_4d(sa, &tmA, bar_full + 8 * stage, kc * KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n);
+            if (!(p.dbg & 1)) tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full + 8 * stage, kc * KC, p.tap_w[t] * p.Nout + nblk * BN);
+            if ((p.dbg & 3) == 3 && elect_one()) mbar_arrive(bar_full + 8 * stage);
             if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; }
           }
         }
@@ -97,7 +99,8 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {   // the WHOLE warp runs this loop (warp-uniform control flow lets ptxas keep descriptors and coordinates in
+        // uniform registers); the issuing wrappers elect one lane
       // descriptors are base + (byte offset >> 4): nothing is rebuilt inside the loop (the issuing thread is
       // instruction-latency bound, profiles/r01_conv_stage1.md)
       constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
@@ -212,7 +215,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   const int pad = p.R / 2;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the WHOLE warp runs this loop (warp-uniform control flow lets ptxas keep descriptors and coordinates in
+        // uniform registers); the issuing wrappers elect one lane
       int bs = 0; uint32_t bph = 0;
       int as = 0; uint32_t aph = 0;
       for (int tile = t_beg; tile < t_end; ++tile) {
@@ -239,7 +243,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the WHOLE warp runs this loop (warp-uniform control flow lets ptxas keep descriptors and coordinates in
+        // uniform registers); the issuing wrappers elect one lane
       const uint32_t idesc = make_idesc(128, p.cin_blk, 1, 1);
       int bs = 0; uint32_t bph = 0;
       int as = 0; uint32_t aph = 0;
@@ -364,6 +369,7 @@ int run_gather(const bf16* in, int N, int Hin, int Win, int Kc,           // gat
   p.total_tiles = p.num_pix_tiles * p.n_blocks;
   p.kchunks = Kc / KC;
   p.Nout = Nout;
+  { const char* e = getenv("SVK_DEBUG_SKIP"); p.dbg = e ? atoi(e) : 0; }
   CUtensorMap ta, tb;
   if (int e = make_nhwc_map(&ta, in, N, Hin, Win, Kc, KC, p.bw, p.bh, es)) return e;
   if (int e = make_w_map(&tb, w, (long long)ntaps_total * Nout, Kc, KC, BN)) return e;

@@ -66,7 +66,8 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {   // the WHOLE warp runs this loop (warp-uniform control flow lets ptxas keep descriptors and coordinates in
+        // uniform registers); the issuing wrappers elect one lane
       mbar_expect_tx(bar_w, w_bytes_all);
       for (int t = 0; t < 9; ++t) tma_load_2d(wsm + t * B_BYTES, &tmB, bar_w, 0, t * p.Nout);
       int stage = 0; uint32_t ph = 0;
@@ -87,7 +88,8 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {   // the WHOLE warp runs this loop (warp-uniform control flow lets ptxas keep descriptors and coordinates in
+        // uniform registers); the issuing wrappers elect one lane
       // The issuing thread is instruction-latency bound (profiles/r01: ~180 cycles per UMMA against a 64-cycle tensor
       // floor when descriptors are rebuilt per MMA), so everything is hoisted: a descriptor is base + (byte offset >> 4)
       // in its low 14-bit address field, and all tap offsets are compile-time multiples of loop-invariant registers.

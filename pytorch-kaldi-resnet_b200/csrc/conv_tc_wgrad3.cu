@@ -67,7 +67,8 @@ conv_tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
   const uint32_t halo_bytes = (uint32_t)(p.bh + 2) * p.bw * ROWB;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the WHOLE warp runs this loop (warp-uniform control flow lets ptxas keep descriptors and coordinates in
+        // uniform registers); the issuing wrappers elect one lane
       int xs = 0; uint32_t xph = 0;
       int ds = 0; uint32_t dph = 0;
       for (int tile = t_beg; tile < t_end; ++tile) {
@@ -90,7 +91,8 @@ conv_tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the WHOLE warp runs this loop (warp-uniform control flow lets ptxas keep descriptors and coordinates in
+        // uniform registers); the issuing wrappers elect one lane
       constexpr uint32_t idesc = make_idesc(128, CK, 1, 1);     // both operands MN-major
       int xs = 0; uint32_t xph = 0;
       int ds = 0; uint32_t dph = 0;
