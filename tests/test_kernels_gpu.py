@@ -357,3 +357,50 @@ def test_decode_script_matches_batch1_oracle():
             ref = O.embed(sd, torch.from_numpy(mat.T.copy()).unsqueeze(0), "mean+std", train=False)[0]
         cos = float(F.cosine_similarity(torch.from_numpy(got[key]).float(), ref, dim=0))
         assert cos >= 0.999, (key, cos)
+
+
+# ------------------------------------------------------------------------------------------------ training CLI
+def test_train_script_end_to_end_then_decode():
+    """The recipe's stage order on synthetic data: train_resnet.py (2 epochs, AAM, mean+std) writes the reference's
+    checkpoint dictionary, the loss goes down, decode.py loads that checkpoint and writes one embedding per utterance;
+    --resume restores model/optimizer/epoch."""
+    import kaldi_io
+    rs = np.random.RandomState(11)
+    n_spk, utts_per_spk, F_ = 4, 6, 40
+    with tempfile.TemporaryDirectory() as d:
+        ark, scp, u2s = os.path.join(d, "feats.ark"), os.path.join(d, "train.scp"), os.path.join(d, "utt2spkid")
+        with open(ark, "wb") as f, open(scp, "w") as s, open(u2s, "w") as u:
+            for spk in range(n_spk):
+                proto = rs.randn(1, F_).astype(np.float32) * 2          # speaker-dependent mean: a learnable task
+                for k in range(utts_per_spk):
+                    key = "spk%d-utt%d" % (spk, k)
+                    mat = (proto + rs.randn(70 + 5 * k, F_)).astype(np.float32)
+                    f.write((key + " ").encode())
+                    s.write("%s %s:%d\n" % (key, ark, f.tell()))
+                    kaldi_io.write_mat(f, mat)
+                    u.write("%s %d\n" % (key, spk))
+        log = os.path.join(d, "exp")
+        base = [sys.executable, os.path.join(util.PKG, "scripts", "train_resnet.py"), "--train-list", scp, "--cv-list", scp,
+                "--utt2spkid", u2s, "--input-dim", "40", "--spk-num", str(n_spk), "--pooling", "mean+std", "--loss-type", "AAM",
+                "--margin", "0.2", "--scale", "30", "--max-chunk-size", "64", "--log-dir", log, "-j", "0", "-b", "8",
+                "--lr", "0.05", "--wd", "1e-4", "-p", "1", "--gpu", "0", "--seed", "3"]
+        r = subprocess.run(base + ["--epochs", "2"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        losses = [float(l.split("Loss")[1].split()[0]) for l in r.stdout.splitlines() if l.startswith("Epoch: [")]
+        assert len(losses) >= 4 and all(np.isfinite(losses)) and min(losses[-3:]) < losses[0]
+        assert " * Acc@1" in r.stdout
+        ck = torch.load(os.path.join(log, "checkpoint_epoch1.pth.tar"), map_location="cpu", weights_only=False)
+        assert sorted(ck) == ["arch", "best_acc1", "epoch", "optimizer", "state_dict"] and ck["epoch"] == 2
+        assert len(ck["state_dict"]) == 219 and "res.layer4.2.bn2.running_var" in ck["state_dict"]
+        assert os.path.exists(os.path.join(log, "model_best.pth.tar"))
+        assert len(ck["optimizer"]["state"]) == 111                    # torch.optim.SGD layout: one momentum buffer per tensor
+        r2 = subprocess.run(base + ["--epochs", "3", "--resume", os.path.join(log, "checkpoint_epoch1.pth.tar")],
+                            capture_output=True, text=True)
+        assert r2.returncode == 0, r2.stderr[-2000:]
+        assert "=> loaded checkpoint" in r2.stdout and "Epoch: [2]" in r2.stdout and "Epoch: [1]" not in r2.stdout
+        r3 = subprocess.run([sys.executable, os.path.join(util.PKG, "scripts", "decode.py"), "--spk_num", str(n_spk), "--input-dim",
+                             "40", "--pooling", "mean+std", "--model-path", os.path.join(log, "model_best.pth.tar"),
+                             "--decode-scp", scp, "--out-path", os.path.join(d, "emb"), "--gpu", "0"], capture_output=True, text=True)
+        assert r3.returncode == 0, r3.stderr[-2000:]
+        emb = dict(kaldi_io.read_vec_flt_ark(os.path.join(d, "emb", "0")))
+        assert len(emb) == n_spk * utts_per_spk and all(v.shape == (256,) and np.isfinite(v).all() for v in emb.values())
