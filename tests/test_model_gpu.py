@@ -301,3 +301,37 @@ def test_wide_variant_train_step_vs_live_oracle():
     lb = CrossEntropyLoss()(mb(x.cuda(), y.cuda()), y.cuda())
     lb.backward()
     assert abs(float(lb) - float(lref.detach())) <= 2e-2 * float(lref.detach())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_loss_trajectory_follows_oracle(precision):
+    """Eight SGD steps on a fixed batch: the CUDA path learns like the reference's algorithm (oracle train_step on the
+    same weights and batch).  fp32: every loss within 2 %; bf16: within 10 %; both end below where they started."""
+    from model import NeuralSpeakerModel
+    from svk.loss import CrossEntropyLoss
+    from svk.optim import SGD
+    torch.manual_seed(5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = NeuralSpeakerModel(spk_num=10, feat_dim=40, pooling="mean+std", loss="AAM", precision=precision)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    g = torch.Generator().manual_seed(6)
+    y = torch.arange(16) % 10
+    x = torch.randn(16, 40, 64, generator=g) + y.view(-1, 1, 1).float() * 0.3          # class-dependent offset: learnable
+    names = O.param_names(sd)
+    bufs = [None] * len(names)
+    ref = [O.train_step(sd, names, x, y, "mean+std", "AAM", 0.2, 30, bufs, 0.02, 0.9, 1e-4)[0] for _ in range(8)]
+    m.train()
+    crit, opt = CrossEntropyLoss(), SGD(m.parameters(), 0.02, momentum=0.9, weight_decay=1e-4)
+    xd, yd = x.cuda(), y.cuda()
+    got = []
+    for _ in range(8):
+        loss = crit(m(xd, yd), yd)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        got.append(float(loss))
+    print(precision, "losses", ["%.3f" % v for v in got], "oracle", ["%.3f" % v for v in ref])
+    tol = 0.02 if precision == "fp32" else 0.10
+    assert all(abs(a - b) <= tol * max(1.0, abs(b)) for a, b in zip(got, ref)), (got, ref)
+    assert got[-1] < got[0] - 0.5 and ref[-1] < ref[0] - 0.5
