@@ -149,8 +149,18 @@ int svk_statspool_bwd(const void* x, const float* dout, void* dx, int N, int H, 
 int svk_sgemm(const float* A, long long a_sm, long long a_sk, const float* B, long long b_sk, long long b_sn,
               float* C, long long ldc, int M, int N, int K, float alpha, float beta, const float* bias,
               void* stream);
-/* out[n] = sum_m x[m,n]  (bias gradient). */
-int svk_colsum(const float* x, float* out, int M, int N, void* stream);
+/* Tensor-core GEMM (tcgen05 kind::tf32, fp32 accumulate): C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]).  a_kmajor / b_kmajor:
+ * 1 = the operand is stored with K contiguous (A[m*lda + k], B[n*ldb + k]); 0 = stored transposed (A[k*lda + m],
+ * B[k*ldb + n]) — the views the backward GEMMs need, consumed without a transposing copy.  lda/ldb must be multiples of
+ * 4 floats.  Small-tile-count problems are split along K into `workspace` (>= svk_gemm_tf32_workspace_bytes) and summed
+ * in a fixed order.  Product-mode replacement of svk_sgemm for fc1 (model.py:384), the AAM cosine GEMM (model.py:485),
+ * their gradients, and the s-norm cohort score matrix (compute_topk_mean_std.py:17). */
+size_t svk_gemm_tf32_workspace_bytes(int M, int N, int K);
+int svk_gemm_tf32(const float* A, long long lda, int a_kmajor, const float* B, long long ldb, int b_kmajor, float* C,
+                  long long ldc, int M, int N, int K, const float* bias, void* workspace, size_t workspace_bytes,
+                  void* stream);
+/* out[n] = sum_m x[m*ld + n]  (bias gradient). */
+int svk_colsum(const float* x, float* out, int M, int N, long long ld, void* stream);
 
 /* ---------------------------------------------------------------- AAM-softmax head ----------------------- */
 /* xhat = x / max(||x||, eps) row-wise; inv[r] = 1/max(||x||,eps).  replaces: F.normalize, model.py:485. */
@@ -162,8 +172,8 @@ int svk_l2norm_rows_bwd(const float* dxhat, const float* xhat, const float* inv,
  * cos_t[b] keeps the raw target cosine for backward.  replaces: model.py:487-499. */
 int svk_aam_margin_fwd(float* cos_logits, const long long* label, float* cos_t, int B, int C, float cos_m,
                        float sin_m, float th, float mm, float s, void* stream);
-/* In place on dlogits[B,C] -> dcos (chain rule through the margin and the scale). */
-int svk_aam_margin_bwd(float* dlogits, const long long* label, const float* cos_t, int B, int C, float cos_m,
+/* In place on dlogits (B rows of C values, row pitch ld >= C) -> dcos (chain rule through the margin and the scale). */
+int svk_aam_margin_bwd(float* dlogits, const long long* label, const float* cos_t, int B, int C, int ld, float cos_m,
                        float sin_m, float th, float s, void* stream);
 /* Cross entropy (mean over batch). loss_rows[b] = lse_b - logits[b,y_b]; lse[b] saved; rank[b] = number of
  * logits strictly greater than the target's (top-k correct iff rank < k).

@@ -68,12 +68,13 @@ SVK_API int svk_aam_margin_fwd(float* z, const long long* label, float* cos_t, i
   return 0;
 }
 __global__ void __launch_bounds__(256) aam_margin_bwd_kernel(float* __restrict__ g, const long long* __restrict__ label,
-                                                             const float* __restrict__ cos_t, int B, int C, float cos_m,
-                                                             float sin_m, float th, float s) {
+                                                             const float* __restrict__ cos_t, int B, int C, int ld,
+                                                             float cos_m, float sin_m, float th, float s) {
   long long n = (long long)B * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i / C), c = (int)(i % C);
-    float v = g[i] * s;
+    float* gp = g + (long long)b * ld + c;
+    float v = *gp * s;
     if ((long long)c == label[b]) {
       float ct = cos_t[b];
       if (ct - th > 0.f) {
@@ -82,14 +83,14 @@ __global__ void __launch_bounds__(256) aam_margin_bwd_kernel(float* __restrict__
         v *= cos_m - sin_m * dsine;
       }
     }
-    g[i] = v;
+    *gp = v;
   }
 }
-SVK_API int svk_aam_margin_bwd(float* g, const long long* label, const float* cos_t, int B, int C, float cos_m,
+SVK_API int svk_aam_margin_bwd(float* g, const long long* label, const float* cos_t, int B, int C, int ld, float cos_m,
                                float sin_m, float th, float s, void* stream) {
-  SVK_REQUIRE(g && label && cos_t && B > 0 && C > 0, SVK_E_BADARG, "aam_margin_bwd: bad args");
+  SVK_REQUIRE(g && label && cos_t && B > 0 && C > 0 && ld >= C, SVK_E_BADARG, "aam_margin_bwd: bad args");
   long long n = (long long)B * C; long long b = (n + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
-  aam_margin_bwd_kernel<<<(int)b, 256, 0, as_stream(stream)>>>(g, label, cos_t, B, C, cos_m, sin_m, th, s);
+  aam_margin_bwd_kernel<<<(int)b, 256, 0, as_stream(stream)>>>(g, label, cos_t, B, C, ld, cos_m, sin_m, th, s);
   SVK_LAUNCH_CHECK("aam_margin_bwd");
   return 0;
 }

@@ -160,16 +160,16 @@ SVK_API int svk_sgemm(const float* A, long long a_sm, long long a_sk, const floa
   return 0;
 }
 
-__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N) {
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, long long ld) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
-  for (int m = 0; m < M; ++m) s += x[(long long)m * N + n];
+  for (int m = 0; m < M; ++m) s += x[(long long)m * ld + n];
   out[n] = s;
 }
-SVK_API int svk_colsum(const float* x, float* out, int M, int N, void* stream) {
-  SVK_REQUIRE(x && out && M > 0 && N > 0, SVK_E_BADARG, "colsum: bad args");
-  colsum_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(x, out, M, N);
+SVK_API int svk_colsum(const float* x, float* out, int M, int N, long long ld, void* stream) {
+  SVK_REQUIRE(x && out && M > 0 && N > 0 && ld >= N, SVK_E_BADARG, "colsum: bad args");
+  colsum_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(x, out, M, N, ld);
   SVK_LAUNCH_CHECK("colsum");
   return 0;
 }

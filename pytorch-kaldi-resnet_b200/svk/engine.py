@@ -292,6 +292,21 @@ class SpeakerNetEngine(object):
         call.svk_bn_act_fwd(x.data_ptr(), sc.data_ptr(), sh.data_ptr(), _ptr(res), _ptr(rsc), _ptr(rsh), relu,
                             out.data_ptr(), M, C, c_dtype_code(x), _stream())
 
+    def _gemm(self, A, lda, a_k, Bm, ldb, b_k, C, ldc, M, N, K, bias=None):
+        """C[M,N] = A[M,K] * B[N,K]^T (+bias).  a_k / b_k: operand stored with K contiguous (else transposed view).
+        Product mode: tcgen05 kind::tf32 GEMM; fp32 validation mode: CUDA-core fp32 GEMM."""
+        st = _stream()
+        if self.precision == "bf16" and lda % 4 == 0 and ldb % 4 == 0:
+            need = lib.load().svk_gemm_tf32_workspace_bytes(M, N, K)
+            ws = self._arena("gemm_ws", ((need + 3) // 4 + 4,), torch.float32) if need else None
+            call.svk_gemm_tf32(A.data_ptr(), lda, 1 if a_k else 0, Bm.data_ptr(), ldb, 1 if b_k else 0, C.data_ptr(), ldc,
+                               M, N, K, _ptr(bias), _ptr(ws), need, st)
+        else:
+            a_sm, a_sk = (lda, 1) if a_k else (1, lda)
+            b_sk, b_sn = (1, ldb) if b_k else (ldb, 1)
+            call.svk_sgemm(A.data_ptr(), a_sm, a_sk, Bm.data_ptr(), b_sk, b_sn, C.data_ptr(), ldc, M, N, K, 1.0, 0.0,
+                           _ptr(bias), st)
+
     # ------------------------------------------------------------------------------------------ training forward
     def forward_train(self, x, y, with_head=True):
         """x: (B, F, T) fp32 CUDA, y: (B,) int64 -> logits (B, spk_num) fp32.  Saves activations for backward."""
@@ -350,8 +365,7 @@ class SpeakerNetEngine(object):
         fc = model.fc1
         E = fc.weight.shape[0]
         emb = self._buf(ws, "emb", (B, E), torch.float32)
-        call.svk_sgemm(pooled.data_ptr(), pdim, 1, fc.weight.data_ptr(), 1, pdim, emb.data_ptr(), E, B, E, pdim, 1.0, 0.0,
-                       fc.bias.data_ptr(), st)
+        self._gemm(pooled, pdim, True, fc.weight, pdim, True, emb, E, B, E, pdim, fc.bias)
         if not with_head:
             return emb.clone()
         sv.update(last=cur, Hl=H, Wl=W, mode=mode, pooled=pooled, emb=emb, pdim=pdim, E=E)
@@ -378,8 +392,7 @@ class SpeakerNetEngine(object):
         C = last.weight.shape[0]
         logits = torch.empty(B, C, dtype=torch.float32, device=self.device)
         if loss == "softmax":
-            call.svk_sgemm(h.data_ptr(), E, 1, last.weight.data_ptr(), 1, E, logits.data_ptr(), C, B, C, E, 1.0, 0.0,
-                           last.bias.data_ptr(), st)
+            self._gemm(h, E, True, last.weight, E, True, logits, C, B, C, E, last.bias)
         else:
             if y is None:
                 raise lib.SvkError("AAM head needs labels: call model(x, y)")
@@ -391,7 +404,7 @@ class SpeakerNetEngine(object):
             cos_t = self._buf(ws, "aam_cos_t", (B,), torch.float32)
             call.svk_l2norm_rows_fwd(h.data_ptr(), xh.data_ptr(), xinv.data_ptr(), B, E, 1e-12, st)
             call.svk_l2norm_rows_fwd(last.weight.data_ptr(), wh.data_ptr(), winv.data_ptr(), C, E, 1e-12, st)
-            call.svk_sgemm(xh.data_ptr(), E, 1, wh.data_ptr(), 1, E, logits.data_ptr(), C, B, C, E, 1.0, 0.0, 0, st)
+            self._gemm(xh, E, True, wh, E, True, logits, C, B, C, E)
             call.svk_aam_margin_fwd(logits.data_ptr(), y.data_ptr(), cos_t.data_ptr(), B, C, last.cos_m, last.sin_m,
                                     last.th, last.mm, float(last.s), st)
             if sv is not None:
@@ -410,18 +423,19 @@ class SpeakerNetEngine(object):
         last = model.last
         gw = self._gview[id(last.weight)]
         h = sv["h"]
+        Cp = dlogits.stride(0)                  # padded row pitch of the upstream-gradient copy
         dh = self._buf(ws, "d_h", (B, E), torch.float32)
         if loss == "softmax":
-            call.svk_sgemm(dlogits.data_ptr(), C, 1, last.weight.data_ptr(), E, 1, dh.data_ptr(), E, B, E, C, 1.0, 0.0, 0, st)
-            call.svk_sgemm(dlogits.data_ptr(), 1, C, h.data_ptr(), E, 1, gw.data_ptr(), E, C, E, B, 1.0, 0.0, 0, st)
-            call.svk_colsum(dlogits.data_ptr(), self._gview[id(last.bias)].data_ptr(), B, C, st)
+            self._gemm(dlogits, Cp, True, last.weight, E, False, dh, E, B, E, C)           # dh = dlogits * W
+            self._gemm(dlogits, Cp, False, h, E, False, gw, E, C, E, B)                    # dW = dlogits^T * h
+            call.svk_colsum(dlogits.data_ptr(), self._gview[id(last.bias)].data_ptr(), B, C, Cp, st)
         else:
-            call.svk_aam_margin_bwd(dlogits.data_ptr(), sv["y"].data_ptr(), sv["cos_t"].data_ptr(), B, C, last.cos_m,
+            call.svk_aam_margin_bwd(dlogits.data_ptr(), sv["y"].data_ptr(), sv["cos_t"].data_ptr(), B, C, Cp, last.cos_m,
                                     last.sin_m, last.th, float(last.s), st)
             dxh = self._buf(ws, "d_xh", (B, E), torch.float32)
             dwh = self._buf(ws, "d_wh", (C, E), torch.float32)
-            call.svk_sgemm(dlogits.data_ptr(), C, 1, sv["wh"].data_ptr(), E, 1, dxh.data_ptr(), E, B, E, C, 1.0, 0.0, 0, st)
-            call.svk_sgemm(dlogits.data_ptr(), 1, C, sv["xh"].data_ptr(), E, 1, dwh.data_ptr(), E, C, E, B, 1.0, 0.0, 0, st)
+            self._gemm(dlogits, Cp, True, sv["wh"], E, False, dxh, E, B, E, C)             # dx_hat = dcos * W_hat
+            self._gemm(dlogits, Cp, False, sv["xh"], E, False, dwh, E, C, E, B)            # dW_hat = dcos^T * x_hat
             call.svk_l2norm_rows_bwd(dxh.data_ptr(), sv["xh"].data_ptr(), sv["xinv"].data_ptr(), dh.data_ptr(), B, E, st)
             call.svk_l2norm_rows_bwd(dwh.data_ptr(), sv["wh"].data_ptr(), sv["winv"].data_ptr(), gw.data_ptr(), C, E, st)
         if loss in ("softmax", "AAM-v1"):
@@ -450,17 +464,24 @@ class SpeakerNetEngine(object):
         ws = sv["ws"]
         B = sv["B"]
         self._bsums.zero_()
-        dlogits = dlogits.contiguous().clone()      # the head backward works in place
+        # private copy of the upstream gradient (the head backward works in place) with a row pitch that is a multiple of
+        # 4 floats, so the tensor-core GEMMs can map it with TMA
+        Bq, Cq = dlogits.shape
+        Cp = (Cq + 3) // 4 * 4
+        pad = self._buf(ws, "d_logits_pad", (Bq, Cp), torch.float32)
+        pad[:, :Cq].copy_(dlogits)
+        if Cp != Cq:
+            pad[:, Cq:].zero_()
+        dlogits = pad[:, :Cq]
         demb = self._head_bwd(dlogits, sv)
         # ---- fc1
         fc = model.fc1
         pdim, E = sv["pdim"], sv["E"]
         pooled = sv["pooled"]
         dpool = self._buf(ws, "d_pool", (B, pdim), torch.float32)
-        call.svk_sgemm(demb.data_ptr(), E, 1, fc.weight.data_ptr(), pdim, 1, dpool.data_ptr(), pdim, B, pdim, E, 1.0, 0.0, 0, st)
-        call.svk_sgemm(demb.data_ptr(), 1, E, pooled.data_ptr(), pdim, 1, self._gview[id(fc.weight)].data_ptr(), pdim,
-                       E, pdim, B, 1.0, 0.0, 0, st)
-        call.svk_colsum(demb.data_ptr(), self._gview[id(fc.bias)].data_ptr(), B, E, st)
+        self._gemm(demb, E, True, fc.weight, pdim, False, dpool, pdim, B, pdim, E)                     # dpool = demb * W
+        self._gemm(demb, E, False, pooled, pdim, False, self._gview[id(fc.weight)], pdim, E, pdim, B)  # dW = demb^T * pooled
+        call.svk_colsum(demb.data_ptr(), self._gview[id(fc.bias)].data_ptr(), B, E, E, st)
         self._bucket_done(0)
         # ---- pooling
         last, Hl, Wl, Cl = sv["last"], sv["Hl"], sv["Wl"], self.c_last
@@ -652,8 +673,7 @@ class SpeakerNetEngine(object):
         fc = model.fc1
         E = fc.weight.shape[0]
         emb = torch.empty(B, E, dtype=torch.float32, device=self.device)
-        call.svk_sgemm(pooled.data_ptr(), pdim, 1, fc.weight.data_ptr(), 1, pdim, emb.data_ptr(), E, B, E, pdim, 1.0, 0.0,
-                       fc.bias.data_ptr(), st)
+        self._gemm(pooled, pdim, True, fc.weight, pdim, True, emb, E, B, E, pdim, fc.bias)
         if not with_head:
             return emb
         return self._head_fwd(emb, y, ws, None, train=False)

@@ -48,11 +48,12 @@ SIGNATURES = {
     "svk_statspool_fwd": [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     "svk_statspool_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "svk_sgemm": [_P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _F, _F, _P, _P],
-    "svk_colsum": [_P, _P, _I, _I, _P],
+    "svk_colsum": [_P, _P, _I, _I, _L, _P],
     "svk_l2norm_rows_fwd": [_P, _P, _P, _I, _I, _F, _P],
     "svk_l2norm_rows_bwd": [_P, _P, _P, _P, _I, _I, _P],
     "svk_aam_margin_fwd": [_P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _P],
-    "svk_aam_margin_bwd": [_P, _P, _P, _I, _I, _F, _F, _F, _F, _P],
+    "svk_aam_margin_bwd": [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _P],
+    "svk_gemm_tf32": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _P, _P, ctypes.c_size_t, _P],
     "svk_ce_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     "svk_ce_bwd": [_P, _P, _P, _P, _F, _P, _I, _I, _P],
     "svk_sgd_step": [_P, _P, _P, _L, _F, _F, _F, _F, _P],
@@ -83,6 +84,8 @@ def load():
     lib.svk_launch_count.restype = c_longlong
     lib.svk_conv2d_wgrad_workspace_bytes.restype = ctypes.c_size_t
     lib.svk_conv2d_wgrad_workspace_bytes.argtypes = [_D]
+    lib.svk_gemm_tf32_workspace_bytes.restype = ctypes.c_size_t
+    lib.svk_gemm_tf32_workspace_bytes.argtypes = [_I, _I, _I]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -202,6 +202,38 @@ def test_sgemm_all_layouts():
             assert util.rel_err(c.cpu(), ref) <= 1e-5
 
 
+@pytest.mark.parametrize("shape", [(256, 5994, 256), (256, 256, 5994), (5994, 256, 256), (256, 256, 2560), (37, 130, 45 * 4),
+                                   (2, 256, 2560)])
+def test_gemm_tf32_all_layouts(shape):
+    """tcgen05 kind::tf32 GEMM (product-mode fc1 / AAM cosine / cohort GEMMs): all four operand layouts, split-K, ragged
+    M/N/K, bias.  tf32 keeps 10 mantissa bits: 2e-3 relative to max |C| is the bound (the bf16-mode tolerance is 2e-2)."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    A, Bm, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    ref = A.double() @ Bm.double().t() + bias.double()
+    pad4 = lambda n: (n + 3) // 4 * 4
+    for a_k in (True, False):
+        for b_k in (True, False):
+            # stored layouts with 16-byte-aligned row pitches
+            if a_k:
+                a = torch.zeros(M, pad4(K)); a[:, :K] = A; lda = pad4(K)
+            else:
+                a = torch.zeros(K, pad4(M)); a[:, :M] = A.t(); lda = pad4(M)
+            if b_k:
+                b = torch.zeros(N, pad4(K)); b[:, :K] = Bm; ldb = pad4(K)
+            else:
+                b = torch.zeros(K, pad4(N)); b[:, :N] = Bm.t(); ldb = pad4(N)
+            ad, bd, biasd = a.cuda(), b.cuda(), bias.cuda()
+            c = torch.full((M, N), float("nan"), device="cuda")
+            need = lib.load().svk_gemm_tf32_workspace_bytes(M, N, K)
+            ws = torch.empty(need // 4 + 4, device="cuda")
+            call.svk_gemm_tf32(ad.data_ptr(), lda, int(a_k), bd.data_ptr(), ldb, int(b_k), c.data_ptr(), N, M, N, K,
+                               biasd.data_ptr(), ws.data_ptr(), need, util.st())
+            torch.cuda.synchronize()
+            assert not torch.isnan(c).any(), (a_k, b_k)
+            assert util.rel_err(c.cpu(), ref) <= 2e-3, (a_k, b_k, util.rel_err(c.cpu(), ref))
+
+
 def test_aam_head_and_cross_entropy():
     from svk.loss import CrossEntropyLoss, accuracy
     g = torch.Generator().manual_seed(6)
@@ -233,7 +265,7 @@ def test_aam_head_and_cross_entropy():
     a_got = accuracy(logits, yd, (1, 5))
     assert [float(a_got[0]), float(a_got[1])] == [float(a_ref[0]), float(a_ref[1])]
     d = lg.grad.clone()
-    call.svk_aam_margin_bwd(d.data_ptr(), yd.data_ptr(), cos_t.data_ptr(), B, C, cos_m, sin_m, th, s, st)
+    call.svk_aam_margin_bwd(d.data_ptr(), yd.data_ptr(), cos_t.data_ptr(), B, C, C, cos_m, sin_m, th, s, st)
     dxh, dwh = torch.empty(B, E, device="cuda"), torch.empty(C, E, device="cuda")
     call.svk_sgemm(d.data_ptr(), C, 1, wh.data_ptr(), E, 1, dxh.data_ptr(), E, B, E, C, 1.0, 0.0, 0, st)
     call.svk_sgemm(d.data_ptr(), 1, C, xh.data_ptr(), E, 1, dwh.data_ptr(), E, C, E, B, 1.0, 0.0, 0, st)
