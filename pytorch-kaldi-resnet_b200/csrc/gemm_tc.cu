@@ -95,10 +95,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t sa = base + stage * G_STAGE;
       const uint32_t sb = sa + GBM * GBK * 4;
-      // K-major: rows of 128 B, 8-row groups 1024 B apart, UMMA K = 8 fp32 = 32 B inside the swizzle row.
-      // MN-major: 32-element atoms 4096 B apart (LBO), 8 k-rows per 1024 B group (SBO), UMMA K = 8 rows = 1024 B.
-      const uint64_t ad0 = AK ? make_desc(sa, 16, 1024, 2) : make_desc(sa, 4096, 1024, 2);
-      const uint64_t bd0 = BK_ ? make_desc(sb, 16, 1024, 2) : make_desc(sb, 4096, 1024, 2);
+      // K-major: SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart, UMMA K = 8 fp32 = 32 B inside the swizzle row.
+      // MN-major: 32-bit operands can only be transposed from the SWIZZLE_128B_BASE32B layout (layout type 1, TMA
+      // "128B_ATOM_32B"): 32-element atoms 4096 B apart (LBO), 4 k-rows per 512 B swizzle group (SBO), UMMA K = 8 rows = 1024 B.
+      const uint64_t ad0 = AK ? make_desc(sa, 16, 1024, 2) : make_desc(sa, 4096, 512, 1);
+      const uint64_t bd0 = BK_ ? make_desc(sb, 16, 1024, 2) : make_desc(sb, 4096, 512, 1);
 #pragma unroll
       for (int k = 0; k < GBK / 8; ++k)
         tc_mma_tf32(tmem_base, ad0 + (uint64_t)(AK ? 2 * k : 64 * k), bd0 + (uint64_t)(BK_ ? 2 * k : 64 * k), idesc,
@@ -159,7 +160,8 @@ __global__ void __launch_bounds__(256) gemm_reduce_kernel(const float* __restric
 }
 
 // 2-D fp32 tensor map: dims {cols (contiguous), rows}, row pitch ld floats (must be a multiple of 4), 128B swizzle.
-int make_f32_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+int make_f32_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows,
+                 bool atom32) {
   EncodeTiledFn enc = get_encode();
   SVK_REQUIRE(enc, SVK_E_DRIVER, "gemm_tf32: cuTensorMapEncodeTiled entry point not available");
   SVK_REQUIRE((ld % 4) == 0 && aligned16(ptr), SVK_E_ALIGN, "gemm_tf32: operand pitch (%lld floats) must be a multiple of 4 and "
@@ -169,8 +171,8 @@ int make_f32_map(CUtensorMap* m, const float* ptr, long long rows, long long col
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SVK_REQUIRE(r == CUDA_SUCCESS, SVK_E_DRIVER, "gemm_tf32: cuTensorMapEncodeTiled failed with %d", (int)r);
   return 0;
 }
@@ -228,10 +230,10 @@ SVK_API int svk_gemm_tf32(const float* A, long long lda, int a_kmajor, const flo
     p.C = C; p.ldc = ldc; p.part_stride = 0; p.bias = bias;
   }
   CUtensorMap ta, tb;
-  if (a_kmajor) { if (int e = make_f32_map(&ta, A, M, K, lda, GBK, GBM)) return e; }      // A[M][K]
-  else { if (int e = make_f32_map(&ta, A, K, M, lda, 32, GBK)) return e; }                // A stored [K][M]
-  if (b_kmajor) { if (int e = make_f32_map(&tb, B, N, K, ldb, GBK, GBN)) return e; }      // B[N][K]
-  else { if (int e = make_f32_map(&tb, B, K, N, ldb, 32, GBK)) return e; }                // B stored [K][N]
+  if (a_kmajor) { if (int e = make_f32_map(&ta, A, M, K, lda, GBK, GBM, false)) return e; }      // A[M][K]
+  else { if (int e = make_f32_map(&ta, A, K, M, lda, 32, GBK, true)) return e; }                // A stored [K][M]
+  if (b_kmajor) { if (int e = make_f32_map(&tb, B, N, K, ldb, GBK, GBN, false)) return e; }      // B[N][K]
+  else { if (int e = make_f32_map(&tb, B, K, N, ldb, 32, GBK, true)) return e; }                // B stored [K][N]
   const int grid = p.m_tiles * p.n_tiles * p.ksplit;
   int rc;
   if (a_kmajor && b_kmajor) rc = launch_gemm<true, true>(ta, tb, p, grid, st);
