@@ -347,8 +347,14 @@ def extras(net, dev):
     scoring.cohort_topk_meanstd(q, coh, topk=300, block_rows=2048, device=dev)
     torch.cuda.synchronize()
     dt_sn = time.perf_counter() - t0
+    scoring.cohort_topk_meanstd(q[:64], coh, topk=300, device=dev, tf32=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    scoring.cohort_topk_meanstd(q, coh, topk=300, block_rows=2048, device=dev, tf32=True)
+    torch.cuda.synchronize()
+    dt_sn_tc = time.perf_counter() - t0
     net.train()
-    return {"snorm_stats_rows_per_sec": 2048 / dt_sn, "snorm_sample": "2,048 embeddings x 50,000-row cohort, top-300 mean/std",
+    return {"snorm_stats_rows_per_sec": 2048 / dt_sn, "snorm_stats_rows_per_sec_tf32": 2048 / dt_sn_tc, "snorm_sample": "2,048 embeddings x 50,000-row cohort, top-300 mean/std",
             "extract_utts_per_sec": len(ds) / dt, "extract_frames_per_sec": float(T.sum()) / dt,
             "extract_sample": "512 of the 4708 cfg2 utterances (%d frames), length-sorted padded batches, H2D included" % int(T.sum()),
             "score_trials_per_sec": 37720 / (e0.elapsed_time(e1) / 10 / 1e3), "score_sample": "37,720 trials, device-resident"}

@@ -44,9 +44,11 @@ def l2_normalize_rows(x, eps=1e-12):
     return out
 
 
-def cohort_topk_meanstd(vecs, cohort, topk=300, block_rows=4096, device="cuda"):
+def cohort_topk_meanstd(vecs, cohort, topk=300, block_rows=4096, device="cuda", tf32=False):
     """For every row v of `vecs`: scores = normalize(cohort) @ normalize(v); top-k; (mean, unbiased std).
-    Both inputs must already be mean-subtracted (compute_topk_mean_std.py:41-48).  Returns (mean, std) tensors."""
+    Both inputs must already be mean-subtracted (compute_topk_mean_std.py:41-48).  Returns (mean, std) tensors.
+    tf32=True computes the score matrix on the tensor cores (tcgen05 kind::tf32; scores within ~2e-4 of fp32, inside
+    the 1e-3 north-star bound); the default keeps exact fp32 products like the reference."""
     X, Cm = _f32(vecs, device), _f32(cohort, device)
     n, D = X.shape
     nc = Cm.shape[0]
@@ -64,7 +66,14 @@ def cohort_topk_meanstd(vecs, cohort, topk=300, block_rows=4096, device="cuda"):
     for lo in range(0, n, block_rows):
         rows = min(block_rows, n - lo)
         xb = Xn[lo:lo + rows]
-        call.svk_sgemm(xb.data_ptr(), D, 1, Cn.data_ptr(), 1, D, scores.data_ptr(), nc, rows, nc, D, 1.0, 0.0, 0, st)
+        if tf32 and D % 4 == 0:
+            from . import lib as _lib
+            need = _lib.load().svk_gemm_tf32_workspace_bytes(rows, nc, D)
+            ws = torch.empty(need // 4 + 4, dtype=torch.float32, device=device) if need else None
+            call.svk_gemm_tf32(xb.data_ptr(), D, 1, Cn.data_ptr(), D, 1, scores.data_ptr(), nc, rows, nc, D, 0,
+                               0 if ws is None else ws.data_ptr(), need, st)
+        else:
+            call.svk_sgemm(xb.data_ptr(), D, 1, Cn.data_ptr(), 1, D, scores.data_ptr(), nc, rows, nc, D, 1.0, 0.0, 0, st)
         call.svk_topk_meanstd(scores.data_ptr(), rows, nc, topk, mean[lo:].data_ptr(), std[lo:].data_ptr(), st)
     return mean, std
 

@@ -312,6 +312,8 @@ def test_scoring_kernels_match_reference_scripts():
     m, sd = scoring.cohort_topk_meanstd(e32, c32, topk=300, block_rows=16)
     assert np.abs(m.cpu().numpy() - fx["topk_mean"]).max() <= 1e-6
     assert np.abs(sd.cpu().numpy() - fx["topk_std"]).max() <= 1e-6
+    m2, sd2 = scoring.cohort_topk_meanstd(e32, c32, topk=300, tf32=True)          # tensor-core score matrix
+    assert np.abs(m2.cpu().numpy() - fx["topk_mean"]).max() <= 1e-3 and np.abs(sd2.cpu().numpy() - fx["topk_std"]).max() <= 1e-3
     sn = scoring.snorm_apply(fx["scores"], fx["ie"], fx["it"], fx["topk_mean"], fx["topk_std"], fx["topk_mean"],
                              fx["topk_std"]).cpu().numpy()
     assert np.abs(sn - fx["snorm"]).max() <= 1e-4
