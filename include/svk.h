@@ -75,6 +75,33 @@ int svk_conv2d_fwd(const svk_conv_desc* d, const void* x, const void* w_fwd, voi
  * (dy is N,Ho,Wo,Cout; dx is N,H,W,Cin).  replaces: cuDNN dgrad under loss.backward(), train_resnet.py:327. */
 int svk_conv2d_dgrad(const svk_conv_desc* d, const void* dy, const void* w_dgrad, void* dx, const void* res,
                      const void* res_m, const void* mask, void* stream);
+/* Data gradient with the first half of the BatchNorm backward of the layer BELOW fused into its epilogue.  dx is the
+ * gradient w.r.t. relu(bn(c) [+ shortcut]); the kernel zeroes it where bn->mask <= 0 (the ReLU mask; mask is the stored
+ * activation, shaped like dx) and, when bn->c is non-NULL, accumulates the two sums BatchNorm's backward needs over the
+ * values it stores:  sums[ch] += sum(dx),  sums[Cin + ch] += sum(dx * (c - mean[ch]) * rstd[ch])  — exactly what
+ * svk_bn_bwd_reduce(dx, mask, c, mean, rstd, ...) would compute in a separate pass over dx, mask and c.
+ * svk_bn_bwd_apply is then called with out = NULL (dx is already masked).  bn == NULL: plain svk_conv2d_dgrad.
+ * Not available for the 1x1/stride-2 accumulate form, nor together with res_m (the epilogue streams at most three
+ * tensors: pass an already-masked gradient as res).  replaces: the ReLU and batch_norm backward nodes autograd runs
+ * after each conv's dgrad under loss.backward(), train_resnet.py:327 (model.py:52-53,56-62). */
+typedef struct svk_bn_bwd_fuse {
+  const void* mask;     /* NHWC, same shape/dtype as dx */
+  const void* c;        /* raw conv output normalised by the BatchNorm (same shape), or NULL: mask only */
+  const float* mean;    /* [Cin] batch mean (c non-NULL) */
+  const float* rstd;    /* [Cin] 1/sqrt(var + eps) */
+  double* sums;         /* [2][Cin], accumulated (zero it first) */
+} svk_bn_bwd_fuse;
+int svk_conv2d_dgrad_bn(const svk_conv_desc* d, const void* dy, const void* w_dgrad, void* dx, const void* res,
+                        const void* res_m, const void* mask, const svk_bn_bwd_fuse* bn, void* stream);
+/* Block-input gradient of a downsample block in one call: dx = dgrad(conv1, 3x3/s2) + dgrad(shortcut conv, 1x1/s2), with
+ * the same optional BatchNorm-backward fusion for the layer below (every dx pixel gets its final value in exactly one
+ * epilogue: the 1x1 launch writes the even/even pixels, the 3x3 launch of that parity class adds them back in).
+ * replaces: the two ConvolutionBackward nodes + the add autograd runs for model.py:59-62 under loss.backward(). */
+int svk_downsample_dgrad_bn(const svk_conv_desc* d_conv1, const void* dy1, const void* w1_dgrad,
+                            const svk_conv_desc* d_convd, const void* dyd, const void* wd_dgrad, void* dx,
+                            const svk_bn_bwd_fuse* bn, void* stream);
+/* g = mask > 0 ? g : 0 in place (n elements; n a multiple of the 16-byte vector width). */
+int svk_relu_mask_inplace(void* g, const void* mask, long long n, int dtype, void* stream);
 /* All convs of a network in ONE launch: table[nconv][6] (int64, device) = {offset of the OIHW weight in `flat_params`
  * (floats), offset of its packed copies in w_fwd/w_dgrad (elements), Cout, Cin, R*R, cumulative element start};
  * total = sum Cout*Cin*R*R.  Same layouts as svk_pack_conv_weight. */
@@ -141,8 +168,9 @@ int svk_add_strided2(void* dx, const void* d, int N, int H, int W, int Ho, int W
  * valid_w (nullable) = per-utterance width.  replaces: model.py:441-455 (+ Flatten :381). */
 int svk_statspool_fwd(const void* x, float* out, int N, int H, int W, int C, int mode, const int* valid_w,
                       int dtype, void* stream);
-int svk_statspool_bwd(const void* x, const float* dout, void* dx, int N, int H, int W, int C, int mode, int dtype,
-                      void* stream);
+/* relu_mask != 0: x is a ReLU output and dx is additionally multiplied by (x > 0) (model.py:62 backward). */
+int svk_statspool_bwd(const void* x, const float* dout, void* dx, int N, int H, int W, int C, int mode, int relu_mask,
+                      int dtype, void* stream);
 /* C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] (+ bias[N]) (+ beta*C); fp32; element (m,k) of op(A) at
  * A[m*a_sm + k*a_sk], element (k,n) of op(B) at B[k*b_sk + n*b_sn].
  * replaces: nn.Linear fc1 (model.py:384) and its backward, F.linear in AAMLayer (model.py:485). */

@@ -285,7 +285,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 int svk_conv2d_fwd_tc(const svk_conv_desc* d, const void* x, const void* w, void* y, double* stats, const float* scale,
                       const float* shift, const void* residual, int relu, const int* valid_wo, cudaStream_t st);
 int svk_conv2d_dgrad_tc(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
-                        const void* res_m, const void* mask, cudaStream_t st);
+                        const void* res_m, const void* mask, const svk_bn_bwd_fuse* bn, cudaStream_t st);
+int svk_downsample_dgrad_tc(const svk_conv_desc* d1, const void* dy1, const void* w1, const svk_conv_desc* dd,
+                            const void* dyd, const void* wd, void* dx, const svk_bn_bwd_fuse* bn, cudaStream_t st);
 int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats, int* ksplit_out,
                         cudaStream_t st);
 size_t svk_conv2d_wgrad_tc_ws_floats(const svk_conv_desc* d);
@@ -319,18 +321,66 @@ SVK_API int svk_conv2d_fwd(const svk_conv_desc* d, const void* x, const void* w,
   return 0;
 }
 
-SVK_API int svk_conv2d_dgrad(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
-                             const void* res_m, const void* mask, void* stream) {
+// finish the contract of the fused epilogue with the stand-alone kernels (validation path)
+static int bn_fuse_compose(const svk_bn_bwd_fuse* bn, void* dx, long long M, int C, int dtype, void* stream) {
+  if (!bn) return 0;
+  if (int e = svk_relu_mask_inplace(dx, bn->mask, M * C, dtype, stream)) return e;
+  if (bn->c)
+    return svk_bn_bwd_reduce(dx, nullptr, bn->c, bn->mean, bn->rstd, nullptr, nullptr, nullptr, bn->sums, M, C, dtype, stream);
+  return 0;
+}
+
+SVK_API int svk_conv2d_dgrad_bn(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
+                                const void* res_m, const void* mask, const svk_bn_bwd_fuse* bn, void* stream) {
   if (int e = check_desc("conv2d_dgrad", d)) return e;
   SVK_REQUIRE(dy && w && dx, SVK_E_BADARG, "conv2d_dgrad: null pointer");
   SVK_REQUIRE((res_m == nullptr) == (mask == nullptr), SVK_E_BADARG, "conv2d_dgrad: res_m and mask go together");
+  if (bn) {
+    SVK_REQUIRE(bn->mask, SVK_E_BADARG, "conv2d_dgrad_bn: mask is required");
+    SVK_REQUIRE(!bn->c || (bn->mean && bn->rstd && bn->sums), SVK_E_BADARG, "conv2d_dgrad_bn: c needs mean, rstd and sums");
+    SVK_REQUIRE(!(d->R == 1 && d->stride == 2), SVK_E_UNSUPPORTED, "conv2d_dgrad_bn: not available for the 1x1/s2 accumulate form");
+    SVK_REQUIRE(d->Cin <= 512, SVK_E_UNSUPPORTED, "conv2d_dgrad_bn: Cin=%d > 512", d->Cin);
+    SVK_REQUIRE(res_m == nullptr, SVK_E_UNSUPPORTED,
+                "conv2d_dgrad_bn: a masked residual cannot be combined with the BatchNorm fusion (the epilogue streams at "
+                "most three tensors); pass an already-masked gradient as res");
+  }
   cudaStream_t st = as_stream(stream);
   if (d->impl == SVK_IMPL_TCGEN05) {
     SVK_REQUIRE(d->dtype == SVK_BF16, SVK_E_UNSUPPORTED, "conv2d_dgrad: tcgen05 path is bf16 only");
-    return svk_conv2d_dgrad_tc(d, dy, w, dx, res, res_m, mask, st);
+    return svk_conv2d_dgrad_tc(d, dy, w, dx, res, res_m, mask, bn, st);
   }
   SVK_REQUIRE(d->impl == SVK_IMPL_SIMT, SVK_E_BADARG, "conv2d_dgrad: bad impl %d", d->impl);
-  return svk_conv2d_dgrad_simt(d, dy, w, dx, res, res_m, mask, st);
+  if (int e = svk_conv2d_dgrad_simt(d, dy, w, dx, res, res_m, mask, st)) return e;
+  return bn_fuse_compose(bn, dx, (long long)d->N * d->H * d->W, d->Cin, d->dtype, stream);
+}
+SVK_API int svk_conv2d_dgrad(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
+                             const void* res_m, const void* mask, void* stream) {
+  return svk_conv2d_dgrad_bn(d, dy, w, dx, res, res_m, mask, nullptr, stream);
+}
+
+SVK_API int svk_downsample_dgrad_bn(const svk_conv_desc* d1, const void* dy1, const void* w1_dgrad, const svk_conv_desc* dd,
+                                    const void* dyd, const void* wd_dgrad, void* dx, const svk_bn_bwd_fuse* bn, void* stream) {
+  if (int e = check_desc("downsample_dgrad", d1)) return e;
+  if (int e = check_desc("downsample_dgrad", dd)) return e;
+  SVK_REQUIRE(dy1 && w1_dgrad && dyd && wd_dgrad && dx, SVK_E_BADARG, "downsample_dgrad: null pointer");
+  SVK_REQUIRE(d1->R == 3 && d1->stride == 2 && dd->R == 1 && dd->stride == 2, SVK_E_BADARG,
+              "downsample_dgrad: expects a 3x3/s2 conv and a 1x1/s2 shortcut conv");
+  SVK_REQUIRE(d1->N == dd->N && d1->H == dd->H && d1->W == dd->W && d1->Cin == dd->Cin && d1->dtype == dd->dtype &&
+              d1->impl == dd->impl, SVK_E_BADARG, "downsample_dgrad: the two convs must share their input");
+  if (bn) {
+    SVK_REQUIRE(bn->mask, SVK_E_BADARG, "downsample_dgrad: mask is required");
+    SVK_REQUIRE(!bn->c || (bn->mean && bn->rstd && bn->sums), SVK_E_BADARG, "downsample_dgrad: c needs mean, rstd and sums");
+    SVK_REQUIRE(d1->Cin <= 512, SVK_E_UNSUPPORTED, "downsample_dgrad: Cin=%d > 512", d1->Cin);
+  }
+  cudaStream_t st = as_stream(stream);
+  if (d1->impl == SVK_IMPL_TCGEN05) {
+    SVK_REQUIRE(d1->dtype == SVK_BF16, SVK_E_UNSUPPORTED, "downsample_dgrad: tcgen05 path is bf16 only");
+    return svk_downsample_dgrad_tc(d1, dy1, w1_dgrad, dd, dyd, wd_dgrad, dx, bn, st);
+  }
+  SVK_REQUIRE(d1->impl == SVK_IMPL_SIMT, SVK_E_BADARG, "downsample_dgrad: bad impl %d", d1->impl);
+  if (int e = svk_conv2d_dgrad_simt(dd, dyd, wd_dgrad, dx, nullptr, nullptr, nullptr, st)) return e;
+  if (int e = svk_conv2d_dgrad_simt(d1, dy1, w1_dgrad, dx, dx, nullptr, nullptr, st)) return e;   // res aliases dx
+  return bn_fuse_compose(bn, dx, (long long)d1->N * d1->H * d1->W, d1->Cin, d1->dtype, stream);
 }
 
 SVK_API size_t svk_conv2d_wgrad_workspace_bytes(const svk_conv_desc* d) {

@@ -35,7 +35,7 @@ struct GatherCfg {
 };
 
 template <int KC, int BN>
-__global__ void __launch_bounds__(GATHER_THREADS, 1)
+__global__ void __launch_bounds__(SVK_GATHER_BOUNDS(BN), 1)
 conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ GatherP p) {
   typedef GatherCfg<KC, BN> Cfg;
@@ -52,13 +52,18 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // arrivals that free an accumulator buffer: one per epilogue warp draining it (8 when two groups split every tile)
+  const uint32_t tempty_count = (p.bn_mask && BN >= 128 && blockDim.x == GATHER_THREADS) ? 8u : 4u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, tempty_count); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (p.scale) {
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
+  }
+  if (p.bn_c) {
+    for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.bn_mean[i]; coef[512 + i] = p.bn_rstd[i]; }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(Cfg::TMEM_COLS) : "memory");
@@ -128,7 +133,13 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else {
-    gather_epilogue<BN>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
+    if (p.bn_mask) {
+      if (BN >= 128 && blockDim.x == GATHER_THREADS)
+        gather_epilogue_bn<BN, (BN >= 128)>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
+      else
+        gather_epilogue_bn<BN, false>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
+    }
+    else gather_epilogue<BN>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -336,7 +347,8 @@ int launch_gather_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP&
     configured = true;
   }
   int grid = p.total_tiles < svk_num_sms() ? p.total_tiles : svk_num_sms();
-  conv_tc_gather_kernel<KC, BN><<<grid, BN <= 64 ? GATHER_THREADS : TC_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
+  // 8 epilogue warps for narrow tiles (their epilogue outlasts their MMAs) and for the fused BatchNorm-backward epilogue
+  conv_tc_gather_kernel<KC, BN><<<grid, (BN <= 64 || p.bn_mask) ? GATHER_THREADS : TC_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
   SVK_LAUNCH_CHECK("conv_tc_gather");
   return 0;
 }
@@ -405,9 +417,48 @@ int svk_conv2d_fwd_tc(const svk_conv_desc* d, const void* x, const void* w, void
   return run_gather((const bf16*)x, d->N, d->H, d->W, d->Cin, (const bf16*)w, d->R * d->R, d->Cout, p, d->stride, st);
 }
 
-int svk_conv2d_dgrad_tc(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
-                        const void* res_m, const void* mask, cudaStream_t st) {
+// Stride-2 data gradient: one launch per output parity class; res00 is the additive tensor of class (0,0), res_rest
+// of the other three.
+static int dgrad_s2_classes(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res00,
+                            const void* res_rest, const void* res_m, const void* mask, const svk_bn_bwd_fuse* bn,
+                            cudaStream_t st) {
   const int pad = d->R / 2;
+  for (int ph = 0; ph < 2; ++ph) {
+    for (int pw = 0; pw < 2; ++pw) {
+      GatherP p{};
+      p.Hc = (d->H - ph + 1) / 2; p.Wc = (d->W - pw + 1) / 2;
+      if (p.Hc <= 0 || p.Wc <= 0) continue;
+      p.in_mul = 1; p.ntaps = 0;
+      for (int r = 0; r < d->R; ++r) {
+        if (((ph + pad - r) & 1) != 0) continue;
+        for (int s = 0; s < d->R; ++s) {
+          if (((pw + pad - s) & 1) != 0) continue;
+          int t = p.ntaps++;
+          p.tap_dh[t] = (ph + pad - r) / 2; p.tap_dw[t] = (pw + pad - s) / 2; p.tap_w[t] = r * d->R + s;   // even numerators
+        }
+      }
+      if (p.ntaps == 0) continue;   // 1x1/s2: only class (0,0) receives gradient
+      p.Hout = d->H; p.Wout = d->W; p.o_mul = 2; p.o_off_h = ph; p.o_off_w = pw;
+      p.out = (bf16*)dx; p.res = (const bf16*)((ph | pw) ? res_rest : res00);
+      p.res_m = (const bf16*)res_m; p.mask = (const bf16*)mask;
+      if (bn) {
+        p.bn_mask = (const bf16*)bn->mask;
+        if (bn->c) { p.bn_c = (const bf16*)bn->c; p.bn_mean = bn->mean; p.bn_rstd = bn->rstd; p.stats = bn->sums; }
+      }
+      if (int e = run_gather((const bf16*)dy, d->N, d->Ho, d->Wo, d->Cout, (const bf16*)w, d->R * d->R, d->Cin, p, 1, st)) return e;
+    }
+  }
+  return 0;
+}
+
+int svk_conv2d_dgrad_tc(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res,
+                        const void* res_m, const void* mask, const svk_bn_bwd_fuse* bn, cudaStream_t st) {
+  const int pad = d->R / 2;
+  auto set_bn = [&](GatherP& p) {
+    if (!bn) return;
+    p.bn_mask = (const bf16*)bn->mask;
+    if (bn->c) { p.bn_c = (const bf16*)bn->c; p.bn_mean = bn->mean; p.bn_rstd = bn->rstd; p.stats = bn->sums; }
+  };
   if (d->stride == 1) {
     GatherP p{};
     p.Hc = d->H; p.Wc = d->W; p.in_mul = 1; p.ntaps = d->R * d->R;
@@ -415,6 +466,7 @@ int svk_conv2d_dgrad_tc(const svk_conv_desc* d, const void* dy, const void* w, v
       for (int s = 0; s < d->R; ++s) { int t = r * d->R + s; p.tap_dh[t] = pad - r; p.tap_dw[t] = pad - s; p.tap_w[t] = t; }
     p.Hout = d->H; p.Wout = d->W; p.o_mul = 1;
     p.out = (bf16*)dx; p.res = (const bf16*)res; p.res_m = (const bf16*)res_m; p.mask = (const bf16*)mask;
+    set_bn(p);
     if (gather3_enabled() && svk_gather3_applicable(d->R, 1, d->Cout, d->Cin))
       return svk_conv3x3s1_gather3_tc(dy, d->N, d->H, d->W, d->Cout, w, d->Cin, 1, p, st);
     return run_gather((const bf16*)dy, d->N, d->Ho, d->Wo, d->Cout, (const bf16*)w, d->R * d->R, d->Cin, p, 1, st);
@@ -429,28 +481,16 @@ int svk_conv2d_dgrad_tc(const svk_conv_desc* d, const void* dy, const void* w, v
       SVK_REQUIRE(e == cudaSuccess, (int)e, "conv2d_dgrad: memset failed: %s", cudaGetErrorString(e));
     }
   }
-  for (int ph = 0; ph < 2; ++ph) {
-    for (int pw = 0; pw < 2; ++pw) {
-      GatherP p{};
-      p.Hc = (d->H - ph + 1) / 2; p.Wc = (d->W - pw + 1) / 2;
-      if (p.Hc <= 0 || p.Wc <= 0) continue;
-      p.in_mul = 1; p.ntaps = 0;
-      for (int r = 0; r < d->R; ++r) {
-        if (((ph + pad - r) & 1) != 0) continue;
-        for (int s = 0; s < d->R; ++s) {
-          if (((pw + pad - s) & 1) != 0) continue;
-          int t = p.ntaps++;
-          // floor division by 2 of (ph + pad - r) which is even (may be negative? ph+pad-r >= 0+1-2 = -1 -> only even values: 0 or 2... or -0)
-          p.tap_dh[t] = (ph + pad - r) / 2; p.tap_dw[t] = (pw + pad - s) / 2; p.tap_w[t] = r * d->R + s;
-        }
-      }
-      if (p.ntaps == 0) continue;   // 1x1/s2: only class (0,0) receives gradient
-      p.Hout = d->H; p.Wout = d->W; p.o_mul = 2; p.o_off_h = ph; p.o_off_w = pw;
-      p.out = (bf16*)dx; p.res = (const bf16*)res; p.res_m = (const bf16*)res_m; p.mask = (const bf16*)mask;
-      if (int e = run_gather((const bf16*)dy, d->N, d->Ho, d->Wo, d->Cout, (const bf16*)w, d->R * d->R, d->Cin, p, 1, st)) return e;
-    }
-  }
-  return 0;
+  return dgrad_s2_classes(d, dy, w, dx, res, res, res_m, mask, bn, st);
+}
+
+// dx = dgrad(conv1: 3x3/s2) + dgrad(convd: 1x1/s2), the block-input gradient of a downsample block, with the optional
+// BatchNorm-backward fusion of the layer below.  The 1x1 launch writes only the (even, even) pixels; the 3x3 launch of
+// that parity class adds them back in (res = dx, same thread reads then writes), the other three classes write fresh.
+int svk_downsample_dgrad_tc(const svk_conv_desc* d1, const void* dy1, const void* w1, const svk_conv_desc* dd,
+                            const void* dyd, const void* wd, void* dx, const svk_bn_bwd_fuse* bn, cudaStream_t st) {
+  if (int e = dgrad_s2_classes(dd, dyd, wd, dx, nullptr, nullptr, nullptr, nullptr, nullptr, st)) return e;
+  return dgrad_s2_classes(d1, dy1, w1, dx, dx, nullptr, nullptr, nullptr, bn, st);
 }
 
 namespace {

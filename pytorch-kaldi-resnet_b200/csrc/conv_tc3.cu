@@ -21,7 +21,7 @@ struct Gather3P {
 // Kc == KC (one K chunk per tap: Cin in {32, 64}).  Tap (r = t, s = l) reads halo rows shifted by t (fprop) or 2 - t (dgrad)
 // and the packed filter tap t*3 + l.
 template <int KC, int BN, bool DGRAD>
-__global__ void __launch_bounds__(GATHER_THREADS, 1)
+__global__ void __launch_bounds__(SVK_GATHER_BOUNDS(BN), 1)
 conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ Gather3P q) {
   constexpr int ROWB = KC * 2;
@@ -46,14 +46,19 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   float* coef = reinterpret_cast<float*>(gbase + auxoff + SMEM_AUX + SCR_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // arrivals that free an accumulator buffer: one per epilogue warp draining it (8 when two groups split every tile)
+  const uint32_t tempty_count = (p.bn_mask && BN >= 128 && blockDim.x == GATHER_THREADS) ? 8u : 4u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < q.n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, tempty_count); }
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (p.scale) {
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
+  }
+  if (p.bn_c) {
+    for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.bn_mean[i]; coef[512 + i] = p.bn_rstd[i]; }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
@@ -128,7 +133,13 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else {
-    gather_epilogue<BN>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
+    if (p.bn_mask) {
+      if (BN >= 128 && blockDim.x == GATHER_THREADS)
+        gather_epilogue_bn<BN, (BN >= 128)>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
+      else
+        gather_epilogue_bn<BN, false>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
+    }
+    else gather_epilogue<BN>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
   }
   tc_fence_before();
   __syncthreads();

@@ -350,6 +350,28 @@ SVK_API int svk_add_masked(const void* a, const void* b, const void* mask, void*
 }
 
 template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) relu_mask_kernel(T* __restrict__ g, const T* __restrict__ mask, long long nvec) {
+  constexpr int V = Vec<T>::N;
+  for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (long long)gridDim.x * blockDim.x) {
+    float x[V], m[V];
+    Vec<T>::load(g + iv * V, x);
+    Vec<T>::load(mask + iv * V, m);
+#pragma unroll
+    for (int i = 0; i < V; ++i) x[i] = (m[i] > 0.f) ? x[i] : 0.f;
+    Vec<T>::store(g + iv * V, x);
+  }
+}
+SVK_API int svk_relu_mask_inplace(void* g, const void* mask, long long n, int dtype, void* stream) {
+  SVK_REQUIRE(g && mask && n > 0, SVK_E_BADARG, "relu_mask_inplace: bad args");
+  SVK_DISPATCH_DTYPE(dtype, "relu_mask_inplace",
+    SVK_REQUIRE(n % Vec<T>::N == 0, SVK_E_ALIGN, "relu_mask_inplace: n=%lld not a multiple of %d", n, Vec<T>::N);
+    long long nvec = n / Vec<T>::N;
+    relu_mask_kernel<T><<<ew_grid(nvec), EW_THREADS, 0, as_stream(stream)>>>((T*)g, (const T*)mask, nvec);)
+  SVK_LAUNCH_CHECK("relu_mask_inplace");
+  return 0;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
 add_strided2_kernel(T* __restrict__ dx, const T* __restrict__ d, int N, int H, int W, int Ho, int Wo, int C) {
   constexpr int V = Vec<T>::N;

@@ -41,16 +41,20 @@ SVK_API int svk_statspool_fwd(const void* x, float* out, int N, int H, int W, in
 
 // dx[n,h,w,c] = dvar * 2 (x - mean) / (W-1) + dsm / (2 sqrt(mean) W)   [mode 1]   |   dmean / W   [mode 0]
 // d sqrt(0) := 0 (the reference's inf is always multiplied by a zero ReLU mask).
+// relu_mask != 0: x is the output of a ReLU and dx is additionally multiplied by (x > 0), i.e. the gradient leaves this
+// kernel already masked for the BatchNorm backward of the last block.
 template <typename T>
 __global__ void __launch_bounds__(256) statspool_bwd_kernel(const T* __restrict__ x, const float* __restrict__ dout,
-                                                            T* __restrict__ dx, int N, int H, int W, int C, int mode) {
+                                                            T* __restrict__ dx, int N, int H, int W, int C, int mode,
+                                                            int relu_mask) {
   long long total = (long long)N * H * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C); long long q = i / C; int h = (int)(q % H); int n = (int)(q / H);
     long long base = (((long long)n * H + h) * W) * C + c;
     if (mode == 0) {
       float g = dout[(long long)n * C * H + (long long)c * H + h] / (float)W;
-      for (int w = 0; w < W; ++w) dx[base + (long long)w * C] = from_f<T>(g);
+      for (int w = 0; w < W; ++w)
+        dx[base + (long long)w * C] = from_f<T>((relu_mask && !(to_f(x[base + (long long)w * C]) > 0.f)) ? 0.f : g);
     } else {
       const T* p = x + base;
       float s = 0.f;
@@ -59,17 +63,20 @@ __global__ void __launch_bounds__(256) statspool_bwd_kernel(const T* __restrict_
       const float* o = dout + (long long)n * C * 2 * H + (long long)c * 2 * H;
       float kv = 2.f * o[h] / (float)(W - 1);
       float km = mean > 0.f ? o[H + h] * 0.5f / (sqrtf(mean) * (float)W) : 0.f;
-      for (int w = 0; w < W; ++w) dx[base + (long long)w * C] = from_f<T>(fmaf(kv, to_f(p[(long long)w * C]) - mean, km));
+      for (int w = 0; w < W; ++w) {
+        const float xv = to_f(p[(long long)w * C]);
+        dx[base + (long long)w * C] = from_f<T>((relu_mask && !(xv > 0.f)) ? 0.f : fmaf(kv, xv - mean, km));
+      }
     }
   }
 }
 SVK_API int svk_statspool_bwd(const void* x, const float* dout, void* dx, int N, int H, int W, int C, int mode,
-                              int dtype, void* stream) {
+                              int relu_mask, int dtype, void* stream) {
   SVK_REQUIRE(x && dout && dx && N > 0 && H > 0 && W > 0 && C > 0 && (mode == 0 || mode == 1), SVK_E_BADARG, "statspool_bwd: bad args");
   long long total = (long long)N * H * C;
   long long b = (total + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
   SVK_DISPATCH_DTYPE(dtype, "statspool_bwd",
-    statspool_bwd_kernel<T><<<(int)b, 256, 0, as_stream(stream)>>>((const T*)x, dout, (T*)dx, N, H, W, C, mode);)
+    statspool_bwd_kernel<T><<<(int)b, 256, 0, as_stream(stream)>>>((const T*)x, dout, (T*)dx, N, H, W, C, mode, relu_mask);)
   SVK_LAUNCH_CHECK("statspool_bwd");
   return 0;
 }

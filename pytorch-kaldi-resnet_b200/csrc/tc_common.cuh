@@ -23,6 +23,9 @@ struct GatherP {
   int relu;
   const int* valid_w;
   double* stats;
+  // dgrad only: BatchNorm-backward fusion (svk_bn_bwd_fuse).  out is zeroed where bn_mask <= 0; with bn_c the statistics
+  // become  stats[ch] += sum(out), stats[Nout + ch] += sum(out * (bn_c - mean[ch]) * rstd[ch])  (mean/rstd staged in coef).
+  const bf16* bn_mask; const bf16* bn_c; const float* bn_mean; const float* bn_rstd;
   int dbg;                    // timing experiments only (SVK_DEBUG_SKIP=1: no filter loads, 2: no activation loads)
 };
 
@@ -88,6 +91,18 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -123,9 +138,22 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
 constexpr int TC_THREADS = 192;                // wgrad kernels: producer warp, MMA warp, 4 epilogue warps
 constexpr int GATHER_THREADS = 320;            // fprop/dgrad kernels: producer, MMA, 2 x 4 epilogue warps (one group per
                                                // TMEM accumulator buffer: a tile's epilogue is latency-bound, ~2x the MMA time)
+#define SVK_GATHER_BOUNDS(BN) GATHER_THREADS
 constexpr int SMEM_AUX = 1024;                 // barriers + tmem pointer
-constexpr int SCR_BYTES = 8 * 32 * 33 * 4;     // per-epilogue-warp transpose scratch
+constexpr int SCR_BYTES = 8 * 32 * 36 * 4;     // per-epilogue-warp transpose scratch (33- or 36-word rows)
 constexpr int COEF_BYTES = 2 * 512 * 4;        // scale/shift staged in smem (Nout <= 512)
+
+// ---- epilogue helpers
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& r, float (&v)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+// Epilogue operands of one (pixel row, 32-channel chunk), as loaded: a = additive tensor (res or res_m), b = a mask tensor
+// (the mask of res_m, else bn_mask), c = bn_c.  They are fetched one or two chunks AHEAD of their use so that the global
+// load latency overlaps the MMAs / the previous chunk instead of stalling the 4 epilogue warps once per chunk.
+struct EpiAux { uint4 a[4], b[4], c[4]; };
+struct EpiTile { long long off; int nblk; bool valid, zero_out; };
 
 // Epilogue of the gather kernels (4 warps): TMEM -> registers -> scale/shift -> +residual -> ReLU -> bf16 -> global, plus the
 // per-channel sum / sum-of-squares of the stored values (BatchNorm batch statistics) reduced through smem.
@@ -141,6 +169,7 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
 #pragma unroll
     for (int c = 0; c < NCH; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
     int stat_blk = -1;
+    const int chl = 2 * (lane & 15) + (lane >> 4);    // channel (within a chunk) whose sums this lane keeps
     int acc = group; uint32_t aph = 0;
     const int m = q * 32 + lane;            // accumulator row = pixel index inside the tile (loop invariant)
     const int i = m / p.bw, j = m - i * p.bw;
@@ -154,8 +183,8 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
         if (stat_blk >= 0) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
-            atomicAdd(&p.stats[stat_blk * BN + c * 32 + lane], (double)s1[c]);
-            atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + lane], (double)s2[c]);
+            atomicAdd(&p.stats[stat_blk * BN + c * 32 + chl], (double)s1[c]);
+            atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + chl], (double)s2[c]);
             s1[c] = 0.f; s2[c] = 0.f;
           }
         }
@@ -211,25 +240,45 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = 0.f;
         }
+        uint32_t packed[16];                 // the 32 output values of this row as stored: bf16x2 words
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          packed[e] = valid ? *reinterpret_cast<uint32_t*>(&h) : 0u;
+        }
         if (valid) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float t8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) t8[e] = v[g * 8 + e];
-            Vec<bf16>::store(p.out + off + c * 32 + g * 8, t8);
-          }
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(p.out + off + c * 32 + g * 8) =
+                make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
         }
         if (p.stats) {
-          // statistics of the values as stored (bf16-rounded); transpose through smem so lane e owns channel e
+          // statistics of the values as stored.  The packed rows are transposed through smem (the kernel is bound by
+          // shared-memory bandwidth, so the bf16x2 words halve what this costs): row l starts at word 16 l + 4 (l / 2),
+          // conflict-free for the 16-byte row writes and for the column reads below, where lane (h, j) sums the channel
+          // pair j over the rows of parity h.
+          uint32_t* row = reinterpret_cast<uint32_t*>(myscr) + 16 * lane + 4 * (lane >> 1);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) myscr[lane * 33 + e] = valid ? round_to<bf16>(v[e]) : 0.f;
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(row + g * 4) = make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
           __syncwarp();
-          float a1 = 0.f, a2 = 0.f;
+          const int hh = lane >> 4, jj = lane & 15;
+          const uint32_t* col = reinterpret_cast<const uint32_t*>(myscr) + jj;
+          float a10 = 0.f, a11 = 0.f, a20 = 0.f, a21 = 0.f;
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) { float x = myscr[rr * 33 + lane]; a1 += x; a2 = fmaf(x, x, a2); }
-          s1[c] += a1; s2[c] += a2;
+          for (int k = 0; k < 16; ++k) {
+            const int rr = 2 * k + hh;
+            const uint32_t wv = col[16 * rr + 4 * k];            // 4 * (rr / 2) == 4 * k
+            const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xffff0000u);
+            a10 += x0; a20 = fmaf(x0, x0, a20);
+            a11 += x1; a21 = fmaf(x1, x1, a21);
+          }
           __syncwarp();
+          a10 += __shfl_xor_sync(0xffffffffu, a10, 16); a11 += __shfl_xor_sync(0xffffffffu, a11, 16);
+          a20 += __shfl_xor_sync(0xffffffffu, a20, 16); a21 += __shfl_xor_sync(0xffffffffu, a21, 16);
+          // lane (h, j) keeps channel 2 j + h of this chunk
+          s1[c] += hh ? a11 : a10;
+          s2[c] += hh ? a21 : a20;
         }
       }
       tc_fence_before();
@@ -241,8 +290,177 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
     if (p.stats && stat_blk >= 0) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        atomicAdd(&p.stats[stat_blk * BN + c * 32 + lane], (double)s1[c]);
-        atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + lane], (double)s2[c]);
+        atomicAdd(&p.stats[stat_blk * BN + c * 32 + chl], (double)s1[c]);
+        atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + chl], (double)s2[c]);
+      }
+    }
+  }
+
+
+// Data-gradient epilogue with the BatchNorm-backward fusion (svk_bn_bwd_fuse): out = (acc [+ res]) * (bn_mask > 0), and,
+// with bn_c, stats[ch] += sum(out), stats[Nout + ch] += sum(out * (bn_c - mean[ch]) * rstd[ch]) over the stored values.
+// Up to three operand streams (res, bn_mask, bn_c) are fetched one or two chunks AHEAD of their use, so their latency
+// overlaps the MMAs instead of stalling the epilogue warps once per chunk.  The (g, c) pairs go through shared memory
+// packed as bf16x2 in ONE transpose: the kernels are bound by shared-memory bandwidth (UMMA operand reads), so the
+// epilogue's own smem traffic is what it costs.
+constexpr int SCR_STRIDE = 36;      // words per scratch row: conflict-free for 16-byte row writes and 4-byte column reads
+// SPLIT (BN >= 128, 8 epilogue warps): both warp groups drain EVERY tile, each one half of its 32-column chunks (four
+// warps cannot issue the fused epilogue of a 128/256-wide tile within its MMA time); otherwise the groups alternate tiles.
+template <int BN, bool SPLIT>
+__device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tmem_base, uint32_t bar_tfull,
+                                                   uint32_t bar_tempty, float* scr, const float* coef, int warp, int lane) {
+    const int q = warp & 3;
+    const int ngroups = ((int)blockDim.x - 64) >> 7;
+    const int group = (warp - 2) >> 2;
+    uint32_t* myscr = reinterpret_cast<uint32_t*>(scr) + (warp - 2) * 32 * SCR_STRIDE;
+    constexpr int NCH = SPLIT ? BN / 64 : BN / 32;     // chunks this warp handles per tile
+    constexpr int DEPTH = 1;                           // chunks of look-ahead
+    const int c_first = SPLIT ? group * NCH : 0;       // first 32-column chunk of this warp inside a tile
+    const bf16* pa = p.res;
+    const bf16* pb = p.bn_mask;
+    const bf16* pc = p.bn_c;
+    float s1[NCH], s2[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+    int stat_blk = -1;
+    int acc = SPLIT ? 0 : group; uint32_t aph = 0;
+    const int m = q * 32 + lane;
+    const int i = m / p.bw, j = m - i * p.bw;
+    const int tstep = SPLIT ? (int)gridDim.x : ngroups * (int)gridDim.x;
+
+    auto tile_info = [&](int tile) {
+      EpiTile t;
+      t.nblk = tile % p.n_blocks;
+      int pt = tile / p.n_blocks;
+      const int tw = pt % p.tiles_w; pt /= p.tiles_w;
+      const int th = pt % p.tiles_h;
+      const int n = pt / p.tiles_h;
+      const int hc = th * p.bh + i, wc = tw * p.bw + j;
+      t.valid = (i < p.bh) && (hc < p.Hc) && (wc < p.Wc);
+      const int oh = hc * p.o_mul + p.o_off_h, ow = wc * p.o_mul + p.o_off_w;
+      t.off = t.valid ? ((((long long)n * p.Hout + oh) * p.Wout + ow) * p.Nout + t.nblk * BN) : 0;
+      t.zero_out = false;
+      return t;
+    };
+    auto issue = [&](EpiAux& A, const EpiTile& t, int c) {
+      if (!t.valid) return;
+      const long long o = t.off + (c_first + c) * 32;
+      if (pa) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) A.a[g] = *reinterpret_cast<const uint4*>(pa + o + g * 8);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) A.b[g] = *reinterpret_cast<const uint4*>(pb + o + g * 8);
+      if (pc) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) A.c[g] = *reinterpret_cast<const uint4*>(pc + o + g * 8);
+      }
+    };
+
+    int tile = SPLIT ? (int)blockIdx.x : (int)(blockIdx.x + group * gridDim.x);
+    if (tile >= p.total_tiles) return;
+    EpiTile cur = tile_info(tile), nxt = cur;
+    EpiAux aux[DEPTH];
+    issue(aux[0], cur, 0);
+    for (; tile < p.total_tiles; tile += tstep) {
+      const bool has_next = tile + tstep < p.total_tiles;
+      if (has_next) nxt = tile_info(tile + tstep);
+      if (pc && stat_blk != cur.nblk) {
+        if (stat_blk >= 0) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            atomicAdd(&p.stats[stat_blk * BN + (c_first + c) * 32 + lane], (double)s1[c]);
+            atomicAdd(&p.stats[p.Nout + stat_blk * BN + (c_first + c) * 32 + lane], (double)s2[c]);
+            s1[c] = 0.f; s2[c] = 0.f;
+          }
+        }
+        stat_blk = cur.nblk;
+      }
+      const bool valid = cur.valid;
+      mbar_wait(bar_tfull + 8 * acc, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        EpiAux& A = aux[c % DEPTH];
+        uint32_t r[32];
+        tc_ld32(taddr + (c_first + c) * 32, r);
+        uint32_t packed[16];                 // the 32 output values of this row, bf16x2, as stored
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v8[8], k8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v8[e] = __uint_as_float(r[g * 8 + e]);
+          if (pa) {
+            float t8[8];
+            bf16x8_to_f32(A.a[g], t8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v8[e] += t8[e];
+          }
+          bf16x8_to_f32(A.b[g], k8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v8[e] = (valid && k8[e] > 0.f) ? v8[e] : 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v8[2 * e], v8[2 * e + 1]);
+            packed[g * 4 + e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(p.out + cur.off + (c_first + c) * 32 + g * 8) =
+                make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+        }
+        if (pc) {
+          // word e of the scratch row = (g_e, c_e) as bf16x2; one transpose, the channel-owning lane does the arithmetic
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t cw[4] = {A.c[g].x, A.c[g].y, A.c[g].z, A.c[g].w};
+            if (!valid) { cw[0] = cw[1] = cw[2] = cw[3] = 0u; }      // rows outside the image were never loaded
+            uint32_t o8[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t gw = packed[g * 4 + e];
+              o8[2 * e] = (gw & 0xffffu) | (cw[e] << 16);
+              o8[2 * e + 1] = (gw >> 16) | (cw[e] & 0xffff0000u);
+            }
+            uint32_t* dst = myscr + lane * SCR_STRIDE + g * 8;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(o8[0], o8[1], o8[2], o8[3]);
+            *reinterpret_cast<uint4*>(dst + 4) = make_uint4(o8[4], o8[5], o8[6], o8[7]);
+          }
+        }
+        // the operands of this chunk are consumed: fetch the chunk DEPTH ahead into the same registers
+        if (c + DEPTH < NCH) issue(A, cur, c + DEPTH);
+        else if (has_next) issue(A, nxt, c + DEPTH - NCH);
+        if (pc) {
+          __syncwarp();
+          const int ch = cur.nblk * BN + (c_first + c) * 32 + lane;
+          const float mu = coef[ch];
+          float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t wv = myscr[rr * SCR_STRIDE + lane];
+            const float gv = __uint_as_float(wv << 16), cv = __uint_as_float(wv & 0xffff0000u);
+            a1 += gv;
+            a2 = fmaf(gv, cv - mu, a2);
+          }
+          __syncwarp();
+          s1[c] += a1; s2[c] += a2 * coef[512 + ch];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (!SPLIT && ngroups == 2) aph ^= 1u;
+      else if (++acc == 2) { acc = 0; aph ^= 1u; }
+      cur = nxt;
+    }
+    if (pc && stat_blk >= 0) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        atomicAdd(&p.stats[stat_blk * BN + (c_first + c) * 32 + lane], (double)s1[c]);
+        atomicAdd(&p.stats[p.Nout + stat_blk * BN + (c_first + c) * 32 + lane], (double)s2[c]);
       }
     }
   }

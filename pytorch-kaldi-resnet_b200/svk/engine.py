@@ -17,6 +17,7 @@ Activations are NHWC, bf16 (product) or fp32 (validation mode); torch is used fo
 plumbing only — every arithmetic step is a libsvk kernel.
 """
 import math
+import os
 
 import torch
 
@@ -84,6 +85,8 @@ class SpeakerNetEngine(object):
         self._param_version = 0
         self._saved = None
         self.grad_ready_cb = None       # called as cb(bucket_index) during backward (data-parallel hook)
+        self.fuse_bn_bwd = os.environ.get("SVK_DISABLE_BN_FUSE", "0") != "1"   # A/B switch for the dgrad-epilogue fusion
+        self.debug_masked = set()       # debug taps that hold the gradient already multiplied by the ReLU mask
         self.debug = None               # tests set this to a dict to capture per-layer gradients (clones)
         self._index_modules()
 
@@ -489,8 +492,24 @@ class SpeakerNetEngine(object):
         gmax = max(gmax, max(t[7].numel() for t in sv["blocks"]))
         gbuf = [self._buf(ws, "g%d" % i, (gmax,)) for i in range(5)]
         dO = gbuf[0][:last.numel()].view(last.shape)
-        call.svk_statspool_bwd(last.data_ptr(), dpool.data_ptr(), dO.data_ptr(), B, Hl, Wl, Cl, sv["mode"], self.dcode, st)
+        call.svk_statspool_bwd(last.data_ptr(), dpool.data_ptr(), dO.data_ptr(), B, Hl, Wl, Cl, sv["mode"],
+                               1 if self.fuse_bn_bwd else 0, self.dcode, st)
         cur_bucket = 1
+        # BatchNorm-backward fusion (svk_conv2d_dgrad_bn): every stride-1 data-gradient epilogue applies the ReLU mask
+        # of the layer below and accumulates that layer's (sum g, sum g*xhat); the stand-alone reduce pass survives only
+        # where a gradient is assembled by several launches (downsample blocks) or comes from the pooling layer.
+        fuse = self.fuse_bn_bwd
+        masked = fuse           # dO already carries the ReLU mask of `out` (the pooling backward applied it)
+        reduced = False         # ... and bn2's sums are already in self._bsums
+        if self.debug is not None:
+            self.debug_masked = set()
+
+        def bn_fuse(mask, c=None, bn=None):
+            if c is None:
+                return lib.BnBwdFuse(mask.data_ptr(), None, None, None, None)
+            _, _, mu, rs = self._coefs(bn)
+            return lib.BnBwdFuse(mask.data_ptr(), c.data_ptr(), mu.data_ptr(), rs.data_ptr(), self._bsums[bn.idx].data_ptr())
+
         # ---- blocks in reverse
         for bi in range(len(self.blocks) - 1, -1, -1):
             b = self.blocks[bi]
@@ -509,39 +528,47 @@ class SpeakerNetEngine(object):
             _, _, mu2, rs2 = self._coefs(b.bn2)
             sums2 = self._bsums[b.bn2.idx]
             g2 = b.bn2.mod
+            omask = 0 if masked else out.data_ptr()
             if cd is not None:
                 _, _, mud, rsd = self._coefs(b.bnd)
                 gd = b.bnd.mod
-                call.svk_bn_bwd_reduce(dO.data_ptr(), out.data_ptr(), c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
+                call.svk_bn_bwd_reduce(dO.data_ptr(), omask, c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
                                        cd.data_ptr(), mud.data_ptr(), rsd.data_ptr(), sums2.data_ptr(), Mo, Co, self.dcode, st)
-                call.svk_bn_bwd_apply(dO.data_ptr(), out.data_ptr(), c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
+                call.svk_bn_bwd_apply(dO.data_ptr(), omask, c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
                                       g2.weight.data_ptr(), dc2.data_ptr(), cd.data_ptr(), mud.data_ptr(), rsd.data_ptr(),
                                       gd.weight.data_ptr(), dcd.data_ptr(), sums2.data_ptr(),
                                       self._gview[id(g2.weight)].data_ptr(), self._gview[id(g2.bias)].data_ptr(),
                                       self._gview[id(gd.weight)].data_ptr(), self._gview[id(gd.bias)].data_ptr(),
                                       Mo, Co, self.dcode, st)
             else:
-                call.svk_bn_bwd_reduce(dO.data_ptr(), out.data_ptr(), c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
-                                       0, 0, 0, sums2.data_ptr(), Mo, Co, self.dcode, st)
-                call.svk_bn_bwd_apply(dO.data_ptr(), out.data_ptr(), c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
+                if not reduced:
+                    call.svk_bn_bwd_reduce(dO.data_ptr(), omask, c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
+                                           0, 0, 0, sums2.data_ptr(), Mo, Co, self.dcode, st)
+                call.svk_bn_bwd_apply(dO.data_ptr(), omask, c2.data_ptr(), mu2.data_ptr(), rs2.data_ptr(),
                                       g2.weight.data_ptr(), dc2.data_ptr(), 0, 0, 0, 0, 0, sums2.data_ptr(),
                                       self._gview[id(g2.weight)].data_ptr(), self._gview[id(g2.bias)].data_ptr(), 0, 0,
                                       Mo, Co, self.dcode, st)
             # conv2: weight gradient + data gradient
             if self.debug is not None:
                 self.debug[b.name] = dO.clone()
+                if masked:
+                    self.debug_masked.add(b.name)
                 self.debug[b.name + ".conv2"] = dc2.clone()
                 if dcd is not None:
                     self.debug[b.name + ".downsample.0"] = dcd.clone()
             self._wgrad(d2, b.conv2, a1, dc2)
-            call.svk_conv2d_dgrad(d2, dc2.data_ptr(), b.conv2.w_dgrad.data_ptr(), da1.data_ptr(), 0, 0, 0, st)
-            # bn1 (+ReLU mask from a1)
+            # bn1 (+ReLU mask from a1): mask and sums come out of conv2's data-gradient epilogue
             _, _, mu1, rs1 = self._coefs(b.bn1)
             sums1 = self._bsums[b.bn1.idx]
             g1 = b.bn1.mod
-            call.svk_bn_bwd_reduce(da1.data_ptr(), a1.data_ptr(), c1.data_ptr(), mu1.data_ptr(), rs1.data_ptr(), 0, 0, 0,
-                                   sums1.data_ptr(), Mo, Co, self.dcode, st)
-            call.svk_bn_bwd_apply(da1.data_ptr(), a1.data_ptr(), c1.data_ptr(), mu1.data_ptr(), rs1.data_ptr(),
+            if fuse:
+                call.svk_conv2d_dgrad_bn(d2, dc2.data_ptr(), b.conv2.w_dgrad.data_ptr(), da1.data_ptr(), 0, 0, 0,
+                                         bn_fuse(a1, c1, b.bn1), st)
+            else:
+                call.svk_conv2d_dgrad(d2, dc2.data_ptr(), b.conv2.w_dgrad.data_ptr(), da1.data_ptr(), 0, 0, 0, st)
+                call.svk_bn_bwd_reduce(da1.data_ptr(), a1.data_ptr(), c1.data_ptr(), mu1.data_ptr(), rs1.data_ptr(), 0, 0, 0,
+                                       sums1.data_ptr(), Mo, Co, self.dcode, st)
+            call.svk_bn_bwd_apply(da1.data_ptr(), 0 if fuse else a1.data_ptr(), c1.data_ptr(), mu1.data_ptr(), rs1.data_ptr(),
                                   g1.weight.data_ptr(), dc1.data_ptr(), 0, 0, 0, 0, 0, sums1.data_ptr(),
                                   self._gview[id(g1.weight)].data_ptr(), self._gview[id(g1.bias)].data_ptr(), 0, 0,
                                   Mo, Co, self.dcode, st)
@@ -549,15 +576,34 @@ class SpeakerNetEngine(object):
                 self.debug[b.name + ".conv1"] = dc1.clone()
             self._wgrad(d1, b.conv1, xin, dc1)
             dx = gbuf[2][:xin.numel()].view(xin.shape)
+            # which BatchNorm consumes dx: the stem's, or bn2 of the block below (whose sums can only be fused when that
+            # block has no downsample BN sharing the gradient)
+            if bi == 0:
+                below = (ws["c0"], self.stem_bn)
+            elif self.blocks[bi - 1].convd is None:
+                below = (sv["blocks"][bi - 1][5], self.blocks[bi - 1].bn2)
+            else:
+                below = None
+            if fuse:
+                bnf = bn_fuse(xin, *below) if below is not None else bn_fuse(xin)
             if cd is not None:
                 self._wgrad(dd, b.convd, xin, dcd)
-                call.svk_conv2d_dgrad(d1, dc1.data_ptr(), b.conv1.w_dgrad.data_ptr(), dx.data_ptr(), 0, 0, 0, st)
-                # 1x1/s2 data gradient accumulates into the block-input gradient (res aliases dx)
-                call.svk_conv2d_dgrad(dd, dcd.data_ptr(), b.convd.w_dgrad.data_ptr(), dx.data_ptr(), dx.data_ptr(), 0, 0, st)
+                if fuse:
+                    call.svk_downsample_dgrad_bn(d1, dc1.data_ptr(), b.conv1.w_dgrad.data_ptr(), dd, dcd.data_ptr(),
+                                                 b.convd.w_dgrad.data_ptr(), dx.data_ptr(), bnf, st)
+                else:
+                    call.svk_conv2d_dgrad(d1, dc1.data_ptr(), b.conv1.w_dgrad.data_ptr(), dx.data_ptr(), 0, 0, 0, st)
+                    # 1x1/s2 data gradient accumulates into the block-input gradient (res aliases dx)
+                    call.svk_conv2d_dgrad(dd, dcd.data_ptr(), b.convd.w_dgrad.data_ptr(), dx.data_ptr(), dx.data_ptr(), 0, 0, st)
+            elif fuse:
+                # identity shortcut: + dO (already masked), then the mask of xin and the sums for the BatchNorm below
+                call.svk_conv2d_dgrad_bn(d1, dc1.data_ptr(), b.conv1.w_dgrad.data_ptr(), dx.data_ptr(), dO.data_ptr(), 0, 0,
+                                         bnf, st)
             else:
                 # identity shortcut: + dO * (out > 0), fused into the dgrad epilogue
                 call.svk_conv2d_dgrad(d1, dc1.data_ptr(), b.conv1.w_dgrad.data_ptr(), dx.data_ptr(), 0, dO.data_ptr(),
                                       out.data_ptr(), st)
+            reduced = fuse and below is not None
             gbuf[0], gbuf[2] = gbuf[2], gbuf[0]
             dO = dx
         # ---- stem
@@ -571,9 +617,11 @@ class SpeakerNetEngine(object):
         _, _, mu, rs = self._coefs(bn)
         sums = self._bsums[bn.idx]
         dc0 = gbuf[1][:c0.numel()].view(c0.shape)
-        call.svk_bn_bwd_reduce(dO.data_ptr(), a0.data_ptr(), c0.data_ptr(), mu.data_ptr(), rs.data_ptr(), 0, 0, 0,
-                               sums.data_ptr(), M, C0, self.dcode, st)
-        call.svk_bn_bwd_apply(dO.data_ptr(), a0.data_ptr(), c0.data_ptr(), mu.data_ptr(), rs.data_ptr(),
+        amask = 0 if masked else a0.data_ptr()
+        if not reduced:
+            call.svk_bn_bwd_reduce(dO.data_ptr(), amask, c0.data_ptr(), mu.data_ptr(), rs.data_ptr(), 0, 0, 0,
+                                   sums.data_ptr(), M, C0, self.dcode, st)
+        call.svk_bn_bwd_apply(dO.data_ptr(), amask, c0.data_ptr(), mu.data_ptr(), rs.data_ptr(),
                               bn.mod.weight.data_ptr(), dc0.data_ptr(), 0, 0, 0, 0, 0, sums.data_ptr(),
                               self._gview[id(bn.mod.weight)].data_ptr(), self._gview[id(bn.mod.bias)].data_ptr(), 0, 0,
                               M, C0, self.dcode, st)

@@ -5,10 +5,15 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvk.so")
+LIB_PATH = os.environ.get("SVK_LIB_PATH") or os.path.join(_HERE, "libsvk.so")     # override: A/B runs of kernel variants
 
 F32, BF16 = 0, 1
 IMPL_SIMT, IMPL_TCGEN05 = 0, 1
+
+
+class BnBwdFuse(Structure):
+    """Mirror of svk_bn_bwd_fuse."""
+    _fields_ = [("mask", c_void_p), ("c", c_void_p), ("mean", c_void_p), ("rstd", c_void_p), ("sums", c_void_p)]
 
 
 class ConvDesc(Structure):
@@ -34,6 +39,9 @@ SIGNATURES = {
     "svk_bn_train_act_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P, _L, _I, _I, _P],
     "svk_conv2d_fwd": [_D, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
     "svk_conv2d_dgrad": [_D, _P, _P, _P, _P, _P, _P, _P],
+    "svk_conv2d_dgrad_bn": [_D, _P, _P, _P, _P, _P, _P, ctypes.POINTER(BnBwdFuse), _P],
+    "svk_downsample_dgrad_bn": [_D, _P, _P, _D, _P, _P, _P, ctypes.POINTER(BnBwdFuse), _P],
+    "svk_relu_mask_inplace": [_P, _P, _L, _I, _P],
     "svk_conv2d_wgrad": [_D, _P, _P, _P, _P, ctypes.c_size_t, _P],
     "svk_stem_conv_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P],
     "svk_stem_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -46,7 +54,7 @@ SIGNATURES = {
     "svk_add_masked": [_P, _P, _P, _P, _L, _I, _P],
     "svk_add_strided2": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "svk_statspool_fwd": [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
-    "svk_statspool_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "svk_statspool_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "svk_sgemm": [_P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _F, _F, _P, _P],
     "svk_colsum": [_P, _P, _I, _I, _L, _P],
     "svk_l2norm_rows_fwd": [_P, _P, _P, _I, _I, _F, _P],

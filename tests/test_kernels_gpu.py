@@ -80,6 +80,92 @@ def test_conv_epilogues(impl):
     assert util.rel_err(dx, util.ref_dgrad(dy, w, H, W, stride) + resm * (mask > 0)) <= 2e-2
 
 
+BN_FUSE_SHAPES = [(40, 200, 32, 32, 3, 1), (20, 100, 64, 64, 3, 1), (10, 50, 128, 128, 3, 1), (5, 25, 256, 256, 3, 1),
+                  (13, 27, 64, 32, 3, 1), (20, 100, 32, 64, 3, 2)]
+
+
+@pytest.mark.parametrize("impl,code", [(lib.IMPL_TCGEN05, lib.BF16), (lib.IMPL_SIMT, lib.BF16), (lib.IMPL_SIMT, lib.F32)])
+@pytest.mark.parametrize("shape", BN_FUSE_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_dgrad_bn_fusion(shape, impl, code):
+    """svk_conv2d_dgrad_bn == svk_conv2d_dgrad -> ReLU mask -> svk_bn_bwd_reduce, on the values it stores."""
+    H, W, ci, co, r, stride = shape
+    N = 3
+    x, w, dy = util.make_case(shape, N, 21, quantize=code == lib.BF16)
+    g = torch.Generator().manual_seed(4)
+    q = util.bf16_round if code == lib.BF16 else (lambda t: t)
+    mask, c, res = [q(torch.randn(N, ci, H, W, generator=g)) for _ in range(3)]
+    mean, rstd = torch.randn(ci, generator=g) * 0.3, torch.rand(ci, generator=g) + 0.5
+    d = lib.make_conv_desc(N, H, W, ci, co, r, stride, code, impl)
+    dyd, (_, wd) = util.nhwc(dy, code), util.pack(w, code)
+    keep = [util.nhwc(t, code) for t in (mask, c, res)]
+    md, rd = mean.cuda(), rstd.cuda()
+    for with_c in (True, False):
+        dx = torch.full((N, H, W, ci), float("nan"), dtype=util.tdtype(code), device="cuda")
+        sums = torch.zeros(2, ci, dtype=torch.float64, device="cuda")
+        bn = lib.BnBwdFuse(keep[0].data_ptr(), keep[1].data_ptr() if with_c else None, md.data_ptr() if with_c else None,
+                           rd.data_ptr() if with_c else None, sums.data_ptr() if with_c else None)
+        call.svk_conv2d_dgrad_bn(d, dyd.data_ptr(), wd.data_ptr(), dx.data_ptr(), keep[2].data_ptr() if with_c else 0, 0, 0,
+                                 bn, util.st())
+        torch.cuda.synchronize()
+        got = util.nchw(dx)
+        ref = (util.ref_dgrad(dy, w, H, W, stride) + (res if with_c else 0)) * (mask > 0)
+        assert util.rel_err(got, ref) <= (2e-2 if code == lib.BF16 else 1e-4)
+        assert float(got[mask <= 0].abs().max()) == 0.0
+        if with_c:      # sums of the STORED gradient
+            gd = got.double()
+            xhat = (c.double() - mean.double().view(1, -1, 1, 1)) * rstd.double().view(1, -1, 1, 1)
+            s_ref = torch.stack([gd.sum((0, 2, 3)), (gd * xhat).sum((0, 2, 3))])
+            assert util.rel_err(sums.cpu(), s_ref) <= 1e-4
+    # bad combinations are refused, not silently computed
+    with pytest.raises(lib.SvkError):
+        call.svk_conv2d_dgrad_bn(d, dyd.data_ptr(), wd.data_ptr(), dx.data_ptr(), 0, keep[2].data_ptr(), keep[0].data_ptr(),
+                                 lib.BnBwdFuse(keep[0].data_ptr(), None, None, None, None), util.st())
+    d1 = lib.make_conv_desc(N, H, W, ci, co, 1, 2, code, impl)
+    with pytest.raises(lib.SvkError):
+        call.svk_conv2d_dgrad_bn(d1, dyd.data_ptr(), wd.data_ptr(), dx.data_ptr(), 0, 0, 0,
+                                 lib.BnBwdFuse(keep[0].data_ptr(), None, None, None, None), util.st())
+
+
+@pytest.mark.parametrize("impl,code", [(lib.IMPL_TCGEN05, lib.BF16), (lib.IMPL_SIMT, lib.F32)])
+@pytest.mark.parametrize("hw", [(40, 200, 32), (20, 100, 64), (10, 50, 128), (9, 27, 32)])
+def test_downsample_block_dgrad(hw, impl, code):
+    """svk_downsample_dgrad_bn == dgrad(3x3/s2) + dgrad(1x1/s2), masked, with the BatchNorm sums of the stored values."""
+    H, W, ci = hw
+    co, N = 2 * ci, 2
+    x, w1, dy1 = util.make_case((H, W, ci, co, 3, 2), N, 31, quantize=code == lib.BF16)
+    _, wd, dyd = util.make_case((H, W, ci, co, 1, 2), N, 32, quantize=code == lib.BF16)
+    g = torch.Generator().manual_seed(6)
+    q = util.bf16_round if code == lib.BF16 else (lambda t: t)
+    mask, c = q(torch.randn(N, ci, H, W, generator=g)), q(torch.randn(N, ci, H, W, generator=g))
+    mean, rstd = torch.randn(ci, generator=g) * 0.3, torch.rand(ci, generator=g) + 0.5
+    d1 = lib.make_conv_desc(N, H, W, ci, co, 3, 2, code, impl)
+    dd = lib.make_conv_desc(N, H, W, ci, co, 1, 2, code, impl)
+    keep = [util.nhwc(dy1, code), util.pack(w1, code)[1], util.nhwc(dyd, code), util.pack(wd, code)[1],
+            util.nhwc(mask, code), util.nhwc(c, code), mean.cuda(), rstd.cuda()]
+    ref0 = util.ref_dgrad(dy1, w1, H, W, 2) + util.ref_dgrad(dyd, wd, H, W, 2)
+    tol = 2e-2 if code == lib.BF16 else 1e-4
+    for mode in ("plain", "mask", "sums"):
+        dx = torch.full((N, H, W, ci), float("nan"), dtype=util.tdtype(code), device="cuda")
+        sums = torch.zeros(2, ci, dtype=torch.float64, device="cuda")
+        bn = None
+        if mode == "mask":
+            bn = lib.BnBwdFuse(keep[4].data_ptr(), None, None, None, None)
+        elif mode == "sums":
+            bn = lib.BnBwdFuse(keep[4].data_ptr(), keep[5].data_ptr(), keep[6].data_ptr(), keep[7].data_ptr(), sums.data_ptr())
+        call.svk_downsample_dgrad_bn(d1, keep[0].data_ptr(), keep[1].data_ptr(), dd, keep[2].data_ptr(), keep[3].data_ptr(),
+                                     dx.data_ptr(), bn, util.st())
+        torch.cuda.synchronize()
+        got = util.nchw(dx)
+        ref = ref0 if mode == "plain" else ref0 * (mask > 0)
+        assert not torch.isnan(got).any()
+        assert util.rel_err(got, ref) <= tol, mode
+        if mode == "sums":
+            gd = got.double()
+            xhat = (c.double() - mean.double().view(1, -1, 1, 1)) * rstd.double().view(1, -1, 1, 1)
+            s_ref = torch.stack([gd.sum((0, 2, 3)), (gd * xhat).sum((0, 2, 3))])
+            assert util.rel_err(sums.cpu(), s_ref) <= 1e-4
+
+
 def test_stem_conv():
     g = torch.Generator().manual_seed(3)
     N, H, W, C = 3, 30, 51, 32
@@ -173,10 +259,14 @@ def test_stats_pooling(mode):
     assert util.rel_err(out.cpu(), ref.detach()) <= 1e-5
     dx = torch.empty_like(xd)
     doutd = dout.cuda()
-    call.svk_statspool_bwd(xd.data_ptr(), doutd.data_ptr(), dx.data_ptr(), N, H, W, C, mode, lib.F32, util.st())
+    call.svk_statspool_bwd(xd.data_ptr(), doutd.data_ptr(), dx.data_ptr(), N, H, W, C, mode, 0, lib.F32, util.st())
     (ref * dout).sum().backward()
     gref = torch.nan_to_num(xr.grad, nan=0.0, posinf=0.0, neginf=0.0) * (x > 0)      # what survives the ReLU mask upstream
     assert util.rel_err(util.nchw(dx) * (x > 0), gref) <= 1e-5
+    dxm = torch.empty_like(xd)                               # the same with the ReLU mask applied by the kernel
+    call.svk_statspool_bwd(xd.data_ptr(), doutd.data_ptr(), dxm.data_ptr(), N, H, W, C, mode, 1, lib.F32, util.st())
+    assert util.rel_err(util.nchw(dxm), gref) <= 1e-5
+    assert float(util.nchw(dxm)[x <= 0].abs().max()) == 0.0
     # per-utterance valid widths
     lens = torch.tensor([13, 7, 10], dtype=torch.int32)
     lensd = lens.cuda()

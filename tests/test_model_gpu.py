@@ -135,7 +135,12 @@ def test_train_step_fp32_matches_reference(case):
     for nm, t in names.items():
         rep.append(("act", nm) + samp_err(util.sample_of(util.nchw(t)), fx["act/" + nm]))
     for nm, t in m.engine.debug.items():
-        rep.append(("dact", nm) + samp_err(util.sample_of(util.nchw(t)), fx["dact/" + nm]))
+        ref = fx["dact/" + nm]
+        if nm in m.engine.debug_masked:     # the fused dgrad epilogue already applied this block's ReLU mask
+            ref = np.array(ref, dtype=np.float64)
+            ref[3:] *= fx["act/" + nm][3:] > 0
+            ref[0] = np.nan                  # the norm in the fixture is that of the unmasked gradient
+        rep.append(("dact", nm) + samp_err(util.sample_of(util.nchw(t)), ref))
     for nm, p in m.named_parameters():
         if nm == "fc1.bias" and not strict:
             # a bias in front of a training-mode BatchNorm1d has an exactly-zero true gradient: the reference's value
@@ -231,6 +236,8 @@ def test_train_step_bf16_layer_local(impl):
             else:
                 dO = util.nchw(eng.debug[p])
                 dx = dx + dO * (out > 0)
+            if eng.blocks[bi - 1].name in eng.debug_masked:    # fused epilogue: gradient stored with the ReLU mask of `cur`
+                dx = dx * (cur > 0)
             upd("dgrad", util.rel_err(dO_in, dx), p + " input gradient")
         cur = out
     print("bf16", impl, "layer-local worst errors:", {k: "%.2e" % v for k, v in worst.items()})
