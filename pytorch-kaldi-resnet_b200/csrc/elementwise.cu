@@ -249,32 +249,41 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
                     const double* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     float* __restrict__ dgammab, float* __restrict__ dbetab, long long nvec, long long M, int C) {
   constexpr int V = Vec<T>::N;
+  extern __shared__ float s_k[];             // [10][C]: mu, rs, k0, k1, k2 and the same for the second BN
   const int lanes_c = C / V;
   long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)(i0 % lanes_c) * V;
   const float invM = 1.f / (float)M;
+  // one thread per channel derives the coefficients of  dc = k0*g - k1 - xhat*k2  once per block; block 0 also
+  // publishes the parameter gradients (dbeta = sum g, dgamma = sum g*xhat)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float s1 = (float)sums[c], s2 = (float)sums[C + c];
+    const float r_ = rstd[c], k = gamma[c] * r_;
+    s_k[c] = mean[c]; s_k[C + c] = r_; s_k[2 * C + c] = k; s_k[3 * C + c] = k * s1 * invM; s_k[4 * C + c] = k * s2 * invM;
+    if (blockIdx.x == 0) {
+      if (dbeta) dbeta[c] = s1;
+      if (dgamma) dgamma[c] = s2;
+    }
+    if (TWO) {
+      const float s3 = (float)sums[2 * C + c];
+      const float rb = rstdb[c], kb = gammab[c] * rb;
+      s_k[5 * C + c] = meanb[c]; s_k[6 * C + c] = rb; s_k[7 * C + c] = kb; s_k[8 * C + c] = kb * s1 * invM;
+      s_k[9 * C + c] = kb * s3 * invM;
+      if (blockIdx.x == 0) {
+        if (dbetab) dbetab[c] = s1;
+        if (dgammab) dgammab[c] = s3;
+      }
+    }
+  }
+  __syncthreads();
   float mu[V], rs[V], k0[V], k1[V], k2[V];    // dc = k0*g - k1 - xhat*k2
   float mub[V], rsb[V], kb0[V], kb1[V], kb2[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    float s1 = (float)sums[c0 + i], s2 = (float)sums[C + c0 + i];
-    mu[i] = mean[c0 + i]; rs[i] = rstd[c0 + i];
-    k0[i] = gamma[c0 + i] * rs[i]; k1[i] = k0[i] * s1 * invM; k2[i] = k0[i] * s2 * invM;
+    const int c = c0 + i;
+    mu[i] = s_k[c]; rs[i] = s_k[C + c]; k0[i] = s_k[2 * C + c]; k1[i] = s_k[3 * C + c]; k2[i] = s_k[4 * C + c];
     if (TWO) {
-      float s3 = (float)sums[2 * C + c0 + i];
-      mub[i] = meanb[c0 + i]; rsb[i] = rstdb[c0 + i];
-      kb0[i] = gammab[c0 + i] * rsb[i]; kb1[i] = kb0[i] * s1 * invM; kb2[i] = kb0[i] * s3 * invM;
-    }
-  }
-  if (i0 < lanes_c) {  // the first C/V threads also publish the parameter gradients
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      if (dbeta) dbeta[c0 + i] = (float)sums[c0 + i];
-      if (dgamma) dgamma[c0 + i] = (float)sums[C + c0 + i];
-      if (TWO) {
-        if (dbetab) dbetab[c0 + i] = (float)sums[c0 + i];
-        if (dgammab) dgammab[c0 + i] = (float)sums[2 * C + c0 + i];
-      }
+      mub[i] = s_k[5 * C + c]; rsb[i] = s_k[6 * C + c]; kb0[i] = s_k[7 * C + c]; kb1[i] = s_k[8 * C + c]; kb2[i] = s_k[9 * C + c];
     }
   }
   for (long long iv = i0; iv < nvec; iv += (long long)gridDim.x * blockDim.x) {
@@ -304,7 +313,8 @@ static void launch_bn_bwd_apply(const void* dout, const void* out, const void* c
                                 float* dgammab, float* dbetab, long long M, int C, cudaStream_t s) {
   long long nvec = M * C / Vec<T>::N;
   int g = ew_grid(nvec);
-#define SVK_BA(MASK_, TWO_) bn_bwd_apply_kernel<T, MASK_, TWO_><<<g, EW_THREADS, 0, s>>>((const T*)dout, (const T*)out, (const T*)c, mean, rstd, gamma, (T*)dc, (const T*)cb, meanb, rstdb, gammab, (T*)dcb, sums, dgamma, dbeta, dgammab, dbetab, nvec, M, C)
+  const size_t sm = (size_t)(cb ? 10 : 5) * C * sizeof(float);
+#define SVK_BA(MASK_, TWO_) bn_bwd_apply_kernel<T, MASK_, TWO_><<<g, EW_THREADS, sm, s>>>((const T*)dout, (const T*)out, (const T*)c, mean, rstd, gamma, (T*)dc, (const T*)cb, meanb, rstdb, gammab, (T*)dcb, sums, dgamma, dbeta, dgammab, dbetab, nvec, M, C)
   if (out && cb) SVK_BA(true, true); else if (out) SVK_BA(true, false); else if (cb) SVK_BA(false, true); else SVK_BA(false, false);
 #undef SVK_BA
 }
@@ -486,27 +496,28 @@ SVK_API int svk_pack_conv_weights_batched(const float* flat, void* wf, void* wd,
 }
 
 // ---------------------------------------------------------------------------------- training BN: finalise + apply fused
-// Every thread derives the coefficients of its own V channels from the fp64 sums (cheap), so the 1-block finalise
-// launch disappears; block 0 also publishes scale/shift/mean/rstd (for backward) and updates the running statistics.
+// Each block derives the coefficients of all C channels once from the fp64 sums into shared memory (one thread per
+// channel), so the 1-block finalise launch disappears and the per-thread preamble is a few smem reads — with every
+// thread deriving its own channels the preamble was ~15 us of a 21 us launch on the small late-stage tensors
+// (profiles/r01_bn_small.md).  Block 0 also publishes scale/shift/mean/rstd (for backward) and updates the running
+// statistics.
 struct BnTrainArgs {
   const double* stats; const float* gamma; const float* beta; float* rm; float* rv; float* coef; 
 };
-template <int V>
-__device__ inline void bn_train_coefs(const BnTrainArgs& a, long long M, int C, int cstride, int c0, float momentum, float eps,
-                                      bool publish, float (&sc)[V], float (&sh)[V]) {
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int c = c0 + i;
+__device__ inline void bn_train_coefs_block(const BnTrainArgs& a, long long M, int C, int cstride, float momentum, float eps,
+                                            bool publish, float* __restrict__ s_sc, float* __restrict__ s_sh) {
+  const double invM = 1.0 / (double)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     // fp64 only where cancellation matters (E[x^2] - E[x]^2); the division / square root run in fp32
-    const double invM = 1.0 / (double)M;           // hoisted by the compiler: loop invariant
     double mean = a.stats[c] * invM;
     double var = fma(-mean, mean, a.stats[C + c] * invM);
     if (var < 0.0) var = 0.0;
     float rstd = 1.0f / sqrtf((float)var + eps);
-    sc[i] = a.gamma[c] * rstd;
-    sh[i] = a.beta[c] - (float)mean * sc[i];
+    float sc = a.gamma[c] * rstd;
+    float sh = a.beta[c] - (float)mean * sc;
+    s_sc[c] = sc; s_sh[c] = sh;
     if (publish) {
-      a.coef[c] = sc[i]; a.coef[cstride + c] = sh[i]; a.coef[2 * cstride + c] = (float)mean; a.coef[3 * cstride + c] = rstd;
+      a.coef[c] = sc; a.coef[cstride + c] = sh; a.coef[2 * cstride + c] = (float)mean; a.coef[3 * cstride + c] = rstd;
       if (a.rm) a.rm[c] = (1.f - momentum) * a.rm[c] + momentum * (float)mean;
       if (a.rv) {
         double unb = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
@@ -520,13 +531,19 @@ __global__ void __launch_bounds__(EW_THREADS)
 bn_train_act_kernel(const T* __restrict__ x, BnTrainArgs a, const T* __restrict__ res, BnTrainArgs b, float momentum,
                     float eps, int relu, T* __restrict__ out, long long nvec, long long M, int C, int cstride) {
   constexpr int V = Vec<T>::N;
+  extern __shared__ float s_coef[];          // [4][C]: scale, shift, (second BN) scale, shift
   const int lanes_c = C / V;
   long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)(i0 % lanes_c) * V;
-  const bool publish = i0 < lanes_c;
+  bn_train_coefs_block(a, M, C, cstride, momentum, eps, blockIdx.x == 0, s_coef, s_coef + C);
+  if (RES == 2) bn_train_coefs_block(b, M, C, cstride, momentum, eps, blockIdx.x == 0, s_coef + 2 * C, s_coef + 3 * C);
+  __syncthreads();
   float sc[V], sh[V], rs[V], rh[V];
-  bn_train_coefs<V>(a, M, C, cstride, c0, momentum, eps, publish, sc, sh);
-  if (RES == 2) bn_train_coefs<V>(b, M, C, cstride, c0, momentum, eps, publish, rs, rh);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sc[i] = s_coef[c0 + i]; sh[i] = s_coef[C + c0 + i];
+    if (RES == 2) { rs[i] = s_coef[2 * C + c0 + i]; rh[i] = s_coef[3 * C + c0 + i]; }
+  }
   for (long long iv = i0; iv < nvec; iv += (long long)gridDim.x * blockDim.x) {
     float v[V], r[V];
     Vec<T>::load(x + iv * V, v);
@@ -554,9 +571,10 @@ SVK_API int svk_bn_train_act_fwd(const void* x, const double* stats, const float
     long long nvec = M * C / Vec<T>::N;
     int g = ew_grid(nvec);
     cudaStream_t s = as_stream(stream);
-    if (!res) bn_train_act_kernel<T, 0><<<g, EW_THREADS, 0, s>>>((const T*)x, a, nullptr, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);
-    else if (!stats_b) bn_train_act_kernel<T, 1><<<g, EW_THREADS, 0, s>>>((const T*)x, a, (const T*)res, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);
-    else bn_train_act_kernel<T, 2><<<g, EW_THREADS, 0, s>>>((const T*)x, a, (const T*)res, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);)
+    const size_t sm = (size_t)4 * C * sizeof(float);
+    if (!res) bn_train_act_kernel<T, 0><<<g, EW_THREADS, sm, s>>>((const T*)x, a, nullptr, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);
+    else if (!stats_b) bn_train_act_kernel<T, 1><<<g, EW_THREADS, sm, s>>>((const T*)x, a, (const T*)res, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);
+    else bn_train_act_kernel<T, 2><<<g, EW_THREADS, sm, s>>>((const T*)x, a, (const T*)res, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);)
   SVK_LAUNCH_CHECK("bn_train_act_fwd");
   return 0;
 }
