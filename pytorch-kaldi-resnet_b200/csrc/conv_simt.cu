@@ -421,13 +421,16 @@ SVK_API int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* 
 
 // ------------------------------------------------------------------------------------------------ stem (Cin = 1)
 // One thread per output pixel, all Cout (<= 64) channels in registers; HBM-bound: reads 4 B, writes 2*Cout B per pixel.
+// The filter sits in shared memory tap-major, so one 16-byte broadcast load feeds four FMAs (with one 4-byte load per
+// FMA the kernel was bound by the load/store unit at 4.5x the HBM time).
 template <typename T, int CO>
 __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        T* __restrict__ y, int N, int H, int W,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        int relu, const int* __restrict__ valid_w) {
-  __shared__ float ws[CO * 9], ss[CO], sb[CO];
-  for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) ws[i] = w[i];
+  __shared__ __align__(16) float ws[9 * CO];     // [tap][channel]
+  __shared__ __align__(16) float ss[CO], sb[CO];
+  for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) ws[(i % 9) * CO + i / 9] = w[i];
   for (int i = threadIdx.x; i < CO; i += blockDim.x) { ss[i] = scale ? scale[i] : 1.f; sb[i] = shift ? shift[i] : 0.f; }
   __syncthreads();
   long long total = (long long)N * H * W;
@@ -448,13 +451,25 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
     for (int c0 = 0; c0 < CO; c0 += V) {
       float o[V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        float acc = 0.f;
+      for (int j = 0; j < V; ++j) o[j] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) acc = fmaf(v[k], ws[(c0 + j) * 9 + k], acc);
-        acc = fmaf(acc, ss[c0 + j], sb[c0 + j]);
-        o[j] = dead ? 0.f : (relu ? fmaxf(acc, 0.f) : acc);
+      for (int k = 0; k < 9; ++k) {
+#pragma unroll
+        for (int j4 = 0; j4 < V; j4 += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&ws[k * CO + c0 + j4]);
+          o[j4] = fmaf(v[k], w4.x, o[j4]); o[j4 + 1] = fmaf(v[k], w4.y, o[j4 + 1]);
+          o[j4 + 2] = fmaf(v[k], w4.z, o[j4 + 2]); o[j4 + 3] = fmaf(v[k], w4.w, o[j4 + 3]);
+        }
       }
+#pragma unroll
+      for (int j4 = 0; j4 < V; j4 += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&ss[c0 + j4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&sb[c0 + j4]);
+        o[j4] = fmaf(o[j4], a4.x, b4.x); o[j4 + 1] = fmaf(o[j4 + 1], a4.y, b4.y);
+        o[j4 + 2] = fmaf(o[j4 + 2], a4.z, b4.z); o[j4 + 3] = fmaf(o[j4 + 3], a4.w, b4.w);
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = dead ? 0.f : (relu ? fmaxf(o[j], 0.f) : o[j]);
       Vec<T>::store(dst + c0, o);
     }
   }
