@@ -42,9 +42,28 @@ def peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the fprop/dgrad kernels from the committed ncu capture of this same command
+    (profiles/summarize_ncu.py over `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`): a static figure measured
+    under the profiler, reported beside the live timings; null when the capture is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_conv_traffic.json")
+    try:
+        with open(path) as f:
+            g = json.load(f)["groups"]
+        ks = [g[k] for k in ("conv_tc_gather_kernel", "conv_tc_gather3_kernel") if k in g]
+        n = sum(k["launches"] for k in ks)
+        by = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks)
+        return {"traffic": by / n, "traffic_unit": "DRAM bytes per launch (ncu, %d launches of one step)" % n,
+                "traffic_source": "profiles/r01_ncu_conv_traffic.json"}
+    except (OSError, KeyError, ValueError, ZeroDivisionError):
+        return {}
+
+
 def conv_flops(tag):
     """Algorithmic FLOPs of one conv launch from its profile tag 'HxW Cin->Cout kR sS NN' (2*MACs, zero padding
     counted as in SURVEY.md §8d: output pixels x Cout x R*R*Cin)."""
+    if " + " in tag:                       # several convs in one call
+        return sum(conv_flops(t) for t in tag.split(" + "))
     hw, ch, k, s, n = tag.split()
     H, W = map(int, hw.split("x"))
     ci, co = map(int, ch.split("->"))
@@ -161,10 +180,18 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    global FRAMES, TRAIN_FLOP_PER_CHUNK, WORKLOAD
     B = args.batch
+    kw = {}
+    if args.workload == "cfg4":      # BASELINE.json config 4: 2x-wide trunk, 300-frame chunks (not the headline; --workload cfg4)
+        FRAMES, TRAIN_FLOP_PER_CHUNK = 300, 81637039104
+        B = args.batch if args.batch != BATCH else 128
+        kw = {"widths": (64, 128, 256, 512)}
+        args.no_extras = args.no_cpu_baseline = True     # those legs describe the headline workload
+        WORKLOAD = "cfg4: 2x-wide ResNet-34 AAM train step, bf16, batch %d/GPU x 300 frames x 40 fbank, 5994 speakers" % B
     torch.manual_seed(1234)
     with contextlib.redirect_stdout(io.StringIO()):
-        net = NeuralSpeakerModel(spk_num=SPK, feat_dim=FEAT, pooling="mean+std", loss="AAM", m=0.2, s=30).cuda(local)
+        net = NeuralSpeakerModel(spk_num=SPK, feat_dim=FEAT, pooling="mean+std", loss="AAM", m=0.2, s=30, **kw).cuda(local)
     model = DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
     crit = CrossEntropyLoss()
     opt = SGD(model.parameters(), 0.1, momentum=0.9, weight_decay=5e-4)
@@ -240,7 +267,7 @@ def run_ours(args):
         agg = {}
         for name, tag, ms in prof:
             key = name
-            if name in ("svk_conv2d_fwd", "svk_conv2d_dgrad"):
+            if name in ("svk_conv2d_fwd", "svk_conv2d_dgrad", "svk_conv2d_dgrad_bn", "svk_downsample_dgrad_bn"):
                 key = "conv_tc_gather(fprop+dgrad)"
             a = agg.setdefault(key, [0.0, 0, 0.0])
             a[0] += ms
@@ -268,6 +295,7 @@ def run_ours(args):
             line["roofline"] = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": tf, "unit": "TFLOP/s",
                                 "frac": ach / tf, "traffic": None, "peak_source": src, "launches": kn,
                                 "avg_launch_ms": kms / kn, "share_of_step": kms / total_prof}
+            line["roofline"].update(ncu_traffic())
         else:
             line["roofline"] = {"bound": "hbm", "kernel": kname, "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None,
                                 "traffic": None, "peak_source": src, "share_of_step": kms / total_prof}
@@ -367,6 +395,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="chunks per GPU per step (256 = BASELINE.json config 3)")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
+                    help="cfg3 = BASELINE.json headline (default); cfg4 = 2x-wide / 300-frame variant, batch 128/GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary extraction / scoring numbers")
     ap.add_argument("--profile-out", default="", help="write the per-(kernel, shape) CUDA-event times of one step here")

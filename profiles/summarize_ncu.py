@@ -31,8 +31,14 @@ def period_of(names):
 
 def main():
     ks = load(sys.argv[1])
-    per = period_of([k["name"] for k in ks])
-    step = ks[:per]
+    names = [k["name"] for k in ks]
+    marks = [i for i, n in enumerate(names) if "sgd_kernel" in n]       # the optimiser kernel closes a training step
+    if len(marks) >= 3:
+        step = ks[marks[1] + 1:marks[2] + 1]
+        per = len(step)
+    else:
+        per = period_of(names)
+        step = ks[:per]
     groups = collections.OrderedDict()
     for k in step:
         base = k["name"].split("<")[0]

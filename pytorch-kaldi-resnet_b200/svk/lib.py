@@ -135,6 +135,9 @@ class _Caller(object):
             if args and isinstance(args[0], ConvDesc):
                 d = args[0]
                 tag = "%dx%d %d->%d k%d s%d N%d" % (d.H, d.W, d.Cin, d.Cout, d.R, d.stride, d.N)
+                for d in args[1:]:          # a second conv in the same call (svk_downsample_dgrad_bn)
+                    if isinstance(d, ConvDesc):
+                        tag += " + %dx%d %d->%d k%d s%d N%d" % (d.H, d.W, d.Cin, d.Cout, d.R, d.stride, d.N)
             PROFILE.append((name, tag, e0, e1))
             if rc != 0:
                 check(rc, name)
