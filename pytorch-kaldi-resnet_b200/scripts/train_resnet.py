@@ -29,6 +29,7 @@ for _p in (_HERE, _PKG):
 
 from datasets import SequenceDataset, SequenceDataset2  # noqa: E402
 from model import NeuralSpeakerModel  # noqa: E402
+from svk.data import DevicePrefetcher  # noqa: E402
 from svk.loss import CrossEntropyLoss, target_rank  # noqa: E402
 from svk.optim import SGD  # noqa: E402
 from svk.parallel import DistributedDataParallel  # noqa: E402
@@ -232,10 +233,10 @@ def train(train_loader, model, criterion, optimizer, epoch, args):
     meters = DeviceMeters(torch.device('cuda', args.gpu))
     bt_sum = dt_sum = 0.0
     end = time.time()
-    for i, (audios, target) in enumerate(train_loader):
+    # batches arrive on the device one step ahead (svk.data.DevicePrefetcher; train_resnet.py:310-311 copied them on the
+    # compute stream)
+    for i, (audios, target) in enumerate(DevicePrefetcher(train_loader, torch.device('cuda', args.gpu))):
         dt = time.time() - end
-        audios = audios.cuda(args.gpu, non_blocking=True)
-        target = target.cuda(args.gpu, non_blocking=True)
         output = model(audios, target)
         loss = criterion(output, target)
         meters.update(loss, target_rank(output, target), audios.size(0))
