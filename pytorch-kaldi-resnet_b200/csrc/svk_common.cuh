@@ -49,10 +49,8 @@ template <typename T> struct Vec;
 template <> struct Vec<float> {
   static constexpr int N = 4;
   typedef float4 raw;
-  __device__ static inline void load(const float* p, float (&v)[4]) {
-    float4 r = *reinterpret_cast<const float4*>(p);
-    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
-  }
+  __device__ static inline void unpack(const float4& r, float (&v)[4]) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+  __device__ static inline void load(const float* p, float (&v)[4]) { unpack(*reinterpret_cast<const float4*>(p), v); }
   __device__ static inline void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -60,8 +58,7 @@ template <> struct Vec<float> {
 template <> struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
   typedef uint4 raw;
-  __device__ static inline void load(const __nv_bfloat16* p, float (&v)[8]) {
-    uint4 r = *reinterpret_cast<const uint4*>(p);
+  __device__ static inline void unpack(const uint4& r, float (&v)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -69,6 +66,7 @@ template <> struct Vec<__nv_bfloat16> {
       v[2 * i] = f.x; v[2 * i + 1] = f.y;
     }
   }
+  __device__ static inline void load(const __nv_bfloat16* p, float (&v)[8]) { unpack(*reinterpret_cast<const uint4*>(p), v); }
   __device__ static inline void store(__nv_bfloat16* p, const float (&v)[8]) {
     uint4 r;
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
