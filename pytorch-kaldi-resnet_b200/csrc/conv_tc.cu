@@ -82,6 +82,8 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // uniform registers); the issuing wrappers elect one lane
       int stage = 0; uint32_t ph = 0;
       const uint32_t a_bytes = (uint32_t)(p.bh * p.bw) * Cfg::ROWB;
+      const bool prof = p.prof != nullptr;
+      long long pw = 0; const long long pt0 = prof ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nblk = tile % p.n_blocks;
         int pt = tile / p.n_blocks;
@@ -91,7 +93,7 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int h0 = th * p.bh * p.in_mul, w0 = tw * p.bw * p.in_mul;
         for (int t = 0; t < p.ntaps; ++t) {
           for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
+            mbar_wait_t(bar_empty + 8 * stage, ph ^ 1u, prof, pw);
             const uint32_t sa = stage0 + stage * Cfg::STAGE;
             mbar_expect_tx(bar_full + 8 * stage, ((p.dbg & 2) ? 0u : a_bytes) + ((p.dbg & 1) ? 0u : (uint32_t)Cfg::B_BYTES));
             if (!(p.dbg & 2)) tma_load_4d(sa, &tmA, bar_full + 8 * stage, kc * KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n);
@@ -101,6 +103,7 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         }
       }
+      if (prof) prof_flush(p.prof, 4, clock64() - pt0, pw, lane);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -113,12 +116,16 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int acc = 0; uint32_t aph = 0;
       const uint64_t a_desc0 = make_desc(stage0, 16, Cfg::SBO, Cfg::LAYOUT);
       uint64_t a_desc = a_desc0;
+      const bool prof = p.prof != nullptr;
+      long long pwf = 0, pwt = 0; const long long pt0 = prof ? clock64() : 0;
+      unsigned long long gt0 = 0;
+      if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
+        mbar_wait_t(bar_tempty + 8 * acc, aph ^ 1u, prof, pwt);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(bar_full + 8 * stage, ph);
+          mbar_wait_t(bar_full + 8 * stage, ph, prof, pwf);
           tc_fence_after();
           const uint64_t b_desc = a_desc + (uint64_t)(Cfg::A_BYTES >> 4);
           tc_mma(d_tmem, a_desc, b_desc, idesc, ks != 0 ? 1u : 0u);
@@ -130,6 +137,12 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         tc_commit(bar_tfull + 8 * acc);
         if (++acc == 2) { acc = 0; aph ^= 1u; }
+      }
+      if (prof && lane == 0) {
+        atomicAdd(p.prof + 0, 1ull); atomicAdd(p.prof + 1, (unsigned long long)(clock64() - pt0));
+        atomicAdd(p.prof + 2, (unsigned long long)pwf); atomicAdd(p.prof + 3, (unsigned long long)pwt);
+        unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        atomicAdd(p.prof + 8, gt1 - gt0); atomicMax(p.prof + 9, ~gt0); atomicMax(p.prof + 10, gt1);   // ns; [9] = ~(earliest start)
       }
     }
   } else {
@@ -382,6 +395,7 @@ int run_gather(const bf16* in, int N, int Hin, int Win, int Kc,           // gat
   p.kchunks = Kc / KC;
   p.Nout = Nout;
   { const char* e = getenv("SVK_DEBUG_SKIP"); p.dbg = e ? atoi(e) : 0; }
+  p.prof = svk_prof_buffer();
   CUtensorMap ta, tb;
   if (int e = make_nhwc_map(&ta, in, N, Hin, Win, Kc, KC, p.bw, p.bh, es)) return e;
   if (int e = make_w_map(&tb, w, (long long)ntaps_total * Nout, Kc, KC, BN)) return e;
@@ -389,6 +403,29 @@ int run_gather(const bf16* in, int N, int Hin, int Win, int Kc,           // gat
 }
 
 }  // namespace
+
+// SVK_PROF=1 (debug): a 16-counter device buffer the gather kernels add their per-role cycle counts to.
+unsigned long long* svk_prof_buffer() {
+  static int on = -1;
+  static unsigned long long* buf = nullptr;
+  if (on < 0) {
+    const char* e = getenv("SVK_PROF");
+    on = (e && e[0] == '1') ? 1 : 0;
+    if (on && (cudaMalloc(&buf, 16 * sizeof(unsigned long long)) != cudaSuccess ||
+               cudaMemset(buf, 0, 16 * sizeof(unsigned long long)) != cudaSuccess)) { buf = nullptr; on = 0; }
+  }
+  return buf;
+}
+// Copies the 16 counters to `out` (host) and clears them; returns SVK_E_UNSUPPORTED unless SVK_PROF=1.
+SVK_API int svk_debug_prof_read(unsigned long long* out) {
+  unsigned long long* b = svk_prof_buffer();
+  SVK_REQUIRE(b != nullptr, SVK_E_UNSUPPORTED, "svk_debug_prof_read: set SVK_PROF=1 before the first convolution call");
+  cudaError_t e = cudaMemcpy(out, b, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  SVK_REQUIRE(e == cudaSuccess, (int)e, "svk_debug_prof_read: %s", cudaGetErrorString(e));
+  e = cudaMemset(b, 0, 16 * sizeof(unsigned long long));
+  SVK_REQUIRE(e == cudaSuccess, (int)e, "svk_debug_prof_read: %s", cudaGetErrorString(e));
+  return 0;
+}
 
 // conv_tc3.cu: resident-filter halo kernel for 3x3/s1 with Cout <= 64
 bool svk_gather3_applicable(int R, int stride, int Kc, int Nout);

@@ -76,6 +76,8 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_expect_tx(bar_w, w_bytes_all);
       for (int t = 0; t < 9; ++t) tma_load_2d(wsm + t * B_BYTES, &tmB, bar_w, 0, t * p.Nout);
       int stage = 0; uint32_t ph = 0;
+      const bool prof = p.prof != nullptr;
+      long long pw = 0; const long long pt0 = prof ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int pt = tile;
         const int tw = pt % p.tiles_w; pt /= p.tiles_w;
@@ -84,12 +86,13 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int h0 = th * p.bh, w0 = tw * p.bw;
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
-          mbar_wait(bar_empty + 8 * stage, ph ^ 1u);
+          mbar_wait_t(bar_empty + 8 * stage, ph ^ 1u, prof, pw);
           mbar_expect_tx(bar_full + 8 * stage, (uint32_t)q.halo_bytes);
           tma_load_4d(stage0 + stage * q.a_stage_bytes, &tmA, bar_full + 8 * stage, 0, w0 + (DGRAD ? 1 - l : l - 1), h0 - 1, n);
           if (++stage == q.n_stages) { stage = 0; ph ^= 1u; }
         }
       }
+      if (prof) prof_flush(p.prof, 4, clock64() - pt0, pw, lane);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -108,13 +111,17 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint64_t a_stage16 = (uint64_t)((uint32_t)q.a_stage_bytes >> 4);
       const uint64_t b_desc0 = make_desc(wsm, 16, SBO, LAYOUT);
       uint64_t a_desc = a_desc0;
+      const bool prof = p.prof != nullptr;
+      long long pwf = 0, pwt = 0; const long long pt0 = prof ? clock64() : 0;
+      unsigned long long gt0 = 0;
+      if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
+        mbar_wait_t(bar_tempty + 8 * acc, aph ^ 1u, prof, pwt);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
-          mbar_wait(bar_full + 8 * stage, ph);
+          mbar_wait_t(bar_full + 8 * stage, ph, prof, pwf);
           tc_fence_after();
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
@@ -130,6 +137,12 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         tc_commit(bar_tfull + 8 * acc);
         if (++acc == 2) { acc = 0; aph ^= 1u; }
+      }
+      if (prof && lane == 0) {
+        atomicAdd(p.prof + 0, 1ull); atomicAdd(p.prof + 1, (unsigned long long)(clock64() - pt0));
+        atomicAdd(p.prof + 2, (unsigned long long)pwf); atomicAdd(p.prof + 3, (unsigned long long)pwt);
+        unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        atomicAdd(p.prof + 8, gt1 - gt0); atomicMax(p.prof + 9, ~gt0); atomicMax(p.prof + 10, gt1);   // ns; [9] = ~(earliest start)
       }
     }
   } else {
@@ -201,6 +214,7 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   p.Nout = Nout;
   p.in_mul = 1;
   p.Hc = Hc; p.Wc = Wc;
+  p.prof = svk_prof_buffer();
   q.g = p;
   for (int l = 0; l < 3; ++l) q.col_dw[l] = dgrad ? 1 - l : l - 1;
   q.halo_bytes = (p.bh + 2) * p.bw * ROWB;

@@ -27,7 +27,11 @@ struct GatherP {
   // become  stats[ch] += sum(out), stats[Nout + ch] += sum(out * (bn_c - mean[ch]) * rstd[ch])  (mean/rstd staged in coef).
   const bf16* bn_mask; const bf16* bn_c; const float* bn_mean; const float* bn_rstd;
   int dbg;                    // timing experiments only (SVK_DEBUG_SKIP=1: no filter loads, 2: no activation loads)
+  unsigned long long* prof;   // SVK_PROF=1: per-role cycle counters (svk_debug_prof_read), else NULL
 };
+// prof[0] CTAs | MMA warp: [1] loop cycles [2] waiting for operands [3] waiting for a free accumulator |
+// producer: [4] loop cycles [5] waiting for a free stage | first epilogue warp: [6] loop cycles [7] waiting for an accumulator
+unsigned long long* svk_prof_buffer();
 
 namespace {
 
@@ -67,6 +71,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       printf("svk conv_tc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       asm volatile("trap;");
     }
+  }
+}
+// mbar_wait that adds the cycles spent waiting to `acc` when profiling
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, long long& acc) {
+  if (!prof) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+__device__ __forceinline__ void prof_flush(unsigned long long* prof, int slot, long long total, long long waited, int lane) {
+  if (prof && lane == 0) {
+    atomicAdd(prof + slot, (unsigned long long)total);
+    atomicAdd(prof + slot + 1, (unsigned long long)waited);
   }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -171,6 +188,8 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
     int stat_blk = -1;
     const int chl = 2 * (lane & 15) + (lane >> 4);    // channel (within a chunk) whose sums this lane keeps
     int acc = group; uint32_t aph = 0;
+    const bool prof = p.prof != nullptr && warp == 2;
+    long long pw = 0; const long long pt0 = prof ? clock64() : 0;
     const int m = q * 32 + lane;            // accumulator row = pixel index inside the tile (loop invariant)
     const int i = m / p.bw, j = m - i * p.bw;
     for (int tile = blockIdx.x + group * gridDim.x; tile < p.total_tiles; tile += ngroups * gridDim.x) {
@@ -197,7 +216,7 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
       bool zero_out = false;
       if (valid && p.valid_w) zero_out = ow >= p.valid_w[n];
 
-      mbar_wait(bar_tfull + 8 * acc, aph);
+      mbar_wait_t(bar_tfull + 8 * acc, aph, prof, pw);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll
@@ -294,6 +313,7 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
         atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + chl], (double)s2[c]);
       }
     }
+    if (prof) prof_flush(p.prof, 6, clock64() - pt0, pw, lane);
   }
 
 
@@ -324,6 +344,8 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
     for (int c = 0; c < NCH; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
     int stat_blk = -1;
     int acc = SPLIT ? 0 : group; uint32_t aph = 0;
+    const bool prof = p.prof != nullptr && warp == 2;
+    long long pw = 0; const long long pt0 = prof ? clock64() : 0;
     const int m = q * 32 + lane;
     const int i = m / p.bw, j = m - i * p.bw;
     const int tstep = SPLIT ? (int)gridDim.x : ngroups * (int)gridDim.x;
@@ -377,7 +399,7 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
         stat_blk = cur.nblk;
       }
       const bool valid = cur.valid;
-      mbar_wait(bar_tfull + 8 * acc, aph);
+      mbar_wait_t(bar_tfull + 8 * acc, aph, prof, pw);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll
@@ -463,6 +485,7 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
         atomicAdd(&p.stats[p.Nout + stat_blk * BN + (c_first + c) * 32 + lane], (double)s2[c]);
       }
     }
+    if (prof) prof_flush(p.prof, 6, clock64() - pt0, pw, lane);
   }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
