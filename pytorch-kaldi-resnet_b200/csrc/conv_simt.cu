@@ -327,6 +327,16 @@ bool svk_wgrad9_applicable(const svk_conv_desc* d);
 size_t svk_conv2d_wgrad9_tc_ws_floats(const svk_conv_desc* d);
 int svk_conv2d_wgrad9_tc(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats, int* ksplit_out,
                          cudaStream_t st);
+// implemented in conv_tc_wgradr.cu (3x3/s1, channels multiples of 128: full-row tiles, filter columns stacked along N)
+bool svk_wgradr_applicable(const svk_conv_desc* d);
+size_t svk_conv2d_wgradr_tc_ws_floats(const svk_conv_desc* d);
+int svk_conv2d_wgradr_tc(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats, int* ksplit_out,
+                         cudaStream_t st);
+static bool wgradr_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVK_DISABLE_WGRADR"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
 static bool wgrad9_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SVK_DISABLE_WGRAD9"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -423,6 +433,7 @@ SVK_API size_t svk_conv2d_wgrad_workspace_bytes(const svk_conv_desc* d) {
   if (check_desc("conv2d_wgrad_workspace_bytes", d)) return 0;
   if (d->impl == SVK_IMPL_TCGEN05) {
     if (wgrad9_enabled() && svk_wgrad9_applicable(d)) return svk_conv2d_wgrad9_tc_ws_floats(d) * sizeof(float);
+    if (wgradr_enabled() && svk_wgradr_applicable(d)) return svk_conv2d_wgradr_tc_ws_floats(d) * sizeof(float);
     if (wgrad3_enabled() && svk_wgrad3_applicable(d)) return svk_conv2d_wgrad3_tc_ws_floats(d) * sizeof(float);
     return svk_conv2d_wgrad_tc_ws_floats(d) * sizeof(float);
   }
@@ -442,6 +453,8 @@ SVK_API int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* 
     SVK_REQUIRE(d->dtype == SVK_BF16, SVK_E_UNSUPPORTED, "conv2d_wgrad: tcgen05 path is bf16 only");
     if (wgrad9_enabled() && svk_wgrad9_applicable(d)) {
       if (int e = svk_conv2d_wgrad9_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
+    } else if (wgradr_enabled() && svk_wgradr_applicable(d)) {
+      if (int e = svk_conv2d_wgradr_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
     } else if (wgrad3_enabled() && svk_wgrad3_applicable(d)) {
       if (int e = svk_conv2d_wgrad3_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
     } else {

@@ -143,6 +143,7 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         atomicAdd(p.prof + 2, (unsigned long long)pwf); atomicAdd(p.prof + 3, (unsigned long long)pwt);
         unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
         atomicAdd(p.prof + 8, gt1 - gt0); atomicMax(p.prof + 9, ~gt0); atomicMax(p.prof + 10, gt1);   // ns; [9] = ~(earliest start)
+        atomicMax(p.prof + 11, gt0); atomicMax(p.prof + 12, ~gt1);                                    // latest start, ~(earliest end)
       }
     }
   } else {

@@ -7,6 +7,7 @@
 //     swizzle atoms).  Per output tile: 3 loads and 0 weight loads instead of 9 + 9.
 // Everything else (TMEM double buffering, epilogue, statistics) is shared with conv_tc.cu.
 #include "tc_common.cuh"
+#include "epilogue_v2.cuh"
 
 namespace {
 
@@ -16,6 +17,12 @@ struct Gather3P {
   int a_stage_bytes;   // halo tile bytes rounded up to 1024
   int halo_bytes;      // bytes one halo TMA load delivers
   int n_stages;
+  // staged epilogue (epilogue_v2.cuh): operand tiles of the epilogue arrive by TMA, the output leaves by TMA
+  int epi2;            // 0: first epilogue (tc_common.cuh)
+  int aux_nbuf;        // aux buffers per epilogue group (2 when they fit)
+  int aux_slots;       // tile slots per aux buffer: 1 (forward: staging only), 2 (mask, c), 3 (mask, c, shortcut gradient)
+  int aux_box_bytes;   // bytes one operand-tile TMA load delivers (bh * bw * BN * 2)
+  int coef_off, aux_off;   // smem offsets (from the 1024-aligned base) of the coefficient table and the aux region
 };
 
 // Kc == KC (one K chunk per tap: Cin in {32, 64}).  Tap (r = t, s = l) reads halo rows shifted by t (fprop) or 2 - t (dgrad)
@@ -23,6 +30,8 @@ struct Gather3P {
 template <int KC, int BN, bool DGRAD>
 __global__ void __launch_bounds__(SVK_GATHER_BOUNDS(BN), 1)
 conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmMask, const __grid_constant__ CUtensorMap tmC,
+                       const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOut,
                        const __grid_constant__ Gather3P q) {
   constexpr int ROWB = KC * 2;
   constexpr int B_BYTES = BN * ROWB;
@@ -41,9 +50,10 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t aux = base + auxoff;
   // aux: full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @144, wfull @160, tmem ptr @176
   const uint32_t bar_full = aux, bar_empty = aux + 64, bar_tfull = aux + 128, bar_tempty = aux + 144, bar_w = aux + 160;
+  const uint32_t bar_afull = aux + 192;                               // staged epilogue: operand tiles of group 0 / 1
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + auxoff + 176);
   float* scr = reinterpret_cast<float*>(gbase + auxoff + SMEM_AUX);
-  float* coef = reinterpret_cast<float*>(gbase + auxoff + SMEM_AUX + SCR_BYTES);
+  float* coef = reinterpret_cast<float*>(gbase + q.coef_off);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // arrivals that free an accumulator buffer: one per epilogue warp draining it (8 when two groups split every tile)
@@ -52,6 +62,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int s = 0; s < q.n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, tempty_count); }
     mbar_init(bar_w, 1);
+    for (int a = 0; a < 4; ++a) mbar_init(bar_afull + 8 * a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (p.scale) {
@@ -143,8 +154,12 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         atomicAdd(p.prof + 2, (unsigned long long)pwf); atomicAdd(p.prof + 3, (unsigned long long)pwt);
         unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
         atomicAdd(p.prof + 8, gt1 - gt0); atomicMax(p.prof + 9, ~gt0); atomicMax(p.prof + 10, gt1);   // ns; [9] = ~(earliest start)
+        atomicMax(p.prof + 11, gt0); atomicMax(p.prof + 12, ~gt1);                                    // latest start, ~(earliest end)
       }
     }
+  } else if (q.epi2) {
+    gather_epilogue_v2<BN>(p, &tmOut, &tmMask, &tmC, &tmRes, tmem_base, bar_tfull, bar_tempty, bar_afull, gbase + q.aux_off,
+                           base + (uint32_t)q.aux_off, q.aux_slots, q.aux_nbuf, q.aux_box_bytes, coef, warp, lane);
   } else {
     if (p.bn_mask) {
       if (BN >= 128 && blockDim.x == GATHER_THREADS)
@@ -162,16 +177,18 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+constexpr int G3_SMEM_MAX = 227 * 1024;
+
 template <int KC, int BN, bool DGRAD>
-int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const Gather3P& q, size_t smem, cudaStream_t st) {
+int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tx, const Gather3P& q, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_gather3_kernel<KC, BN, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_gather3_kernel<KC, BN, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM_MAX);
     SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc3: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     configured = true;
   }
   int grid = q.g.total_tiles < svk_num_sms() ? q.g.total_tiles : svk_num_sms();
-  conv_tc_gather3_kernel<KC, BN, DGRAD><<<grid, GATHER_THREADS, smem, st>>>(ta, tb, q);
+  conv_tc_gather3_kernel<KC, BN, DGRAD><<<grid, GATHER_THREADS, smem, st>>>(ta, tb, tx[0], tx[1], tx[2], tx[3], q);
   SVK_LAUNCH_CHECK("conv_tc_gather3");
   return 0;
 }
@@ -222,16 +239,56 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   int need_rows = 2 * p.bw + 128;
   int rows = (p.bh + 2) * p.bw > need_rows ? (p.bh + 2) * p.bw : need_rows;
   q.a_stage_bytes = (rows * ROWB + 1023) / 1024 * 1024;
-  const size_t fixed = (size_t)9 * Kc * Nout * 2 + SMEM_AUX + SCR_BYTES + COEF_BYTES + 1024;
-  int ns = (int)((200 * 1024 - fixed) / q.a_stage_bytes);
+  // staged epilogue: training forward (statistics, no scale / residual / ReLU) and the fused BatchNorm-backward dgrad
+  static int epi2_on = -1;
+  if (epi2_on < 0) { const char* e = getenv("SVK_DISABLE_EPI2"); epi2_on = (e && e[0] == '1') ? 0 : 1; }
+  const bool fwd_mode = !dgrad && p.stats && !p.scale && !p.res && !p.res_m && !p.relu && !p.valid_w && !p.bn_mask;
+  const bool bwd_mode = dgrad && p.bn_mask && !p.res_m && !p.scale && !p.valid_w && !p.relu;
+  // Measured inside the training step (profiles/r02_epilogue_v2.md): the staged epilogue wins where the first one is bound
+  // by L1 wavefronts — the fused data gradient of the 64-channel stage (0.95 -> 0.74 ms per step) — and loses where a tile's
+  // MMA time (32 channels: ~1,200 cycles) is shorter than its fixed barrier / store latencies, and in the forward pass.
+  // SVK_EPI2=all enables it everywhere it is implemented (A/B runs).
+  static int epi2_all = -1;
+  if (epi2_all < 0) { const char* e = getenv("SVK_EPI2"); epi2_all = (e && e[0] == 'a') ? 1 : 0; }
+  q.epi2 = (epi2_on && ((bwd_mode && Nout == 64) || (epi2_all && (fwd_mode || bwd_mode)))) ? 1 : 0;
+  const size_t w_bytes = (size_t)9 * Kc * Nout * 2;
+  size_t fixed = w_bytes + SMEM_AUX + SCR_BYTES + COEF_BYTES + 1024;
+  size_t limit = 200 * 1024;
+  q.coef_off = 0; q.aux_off = 0;      // filled in below (they depend on the stage count)
+  if (q.epi2) {
+    q.aux_slots = p.res ? 3 : (p.bn_c ? 2 : 1);
+    q.aux_box_bytes = p.bh * p.bw * Nout * 2;
+    const size_t buf_bytes = (size_t)q.aux_slots * 128 * Nout * 2;
+    const size_t fixed0 = w_bytes + SMEM_AUX + COEF_BYTES + 1024 /* align aux */ + 1024 /* align base */;
+    if ((G3_SMEM_MAX - fixed0 - 4 * buf_bytes) / q.a_stage_bytes >= 3 && G3_SMEM_MAX > fixed0 + 4 * buf_bytes) {
+      q.aux_nbuf = 2; fixed = fixed0 + 4 * buf_bytes; limit = G3_SMEM_MAX;
+    } else if ((G3_SMEM_MAX - fixed0 - 2 * buf_bytes) / q.a_stage_bytes >= 2 && G3_SMEM_MAX > fixed0 + 2 * buf_bytes) {
+      q.aux_nbuf = 1; fixed = fixed0 + 2 * buf_bytes; limit = G3_SMEM_MAX;
+    } else {
+      q.epi2 = 0;                     // not enough room next to the resident filter: first epilogue
+    }
+  }
+  int ns = (int)((limit - fixed) / q.a_stage_bytes);
   if (ns > 6) ns = 6;
   SVK_REQUIRE(ns >= 2, SVK_E_UNSUPPORTED, "conv_tc3: not enough shared memory for 2 stages");
   q.n_stages = ns;
   const size_t smem = fixed + (size_t)ns * q.a_stage_bytes;
-  CUtensorMap ta, tb;
+  {
+    const size_t auxbar = (size_t)ns * q.a_stage_bytes + w_bytes;
+    q.coef_off = (int)(auxbar + SMEM_AUX + (q.epi2 ? 0 : SCR_BYTES));
+    q.aux_off = (int)((q.coef_off + COEF_BYTES + 1023) / 1024 * 1024);
+  }
+  CUtensorMap ta, tb, tx[4];
   if (int e = make_nhwc_map(&ta, in, N, Hc, Wc, Kc, KC, p.bw, p.bh + 2, 1)) return e;
   if (int e = make_w_map(&tb, w_packed, (long long)9 * Nout, Kc, KC, BN)) return e;
-#define SVK_L3(K_, N_) if (KC == K_ && BN == N_) return dgrad ? launch3<K_, N_, true>(ta, tb, q, smem, st) : launch3<K_, N_, false>(ta, tb, q, smem, st)
+  for (int k = 0; k < 4; ++k) tx[k] = ta;            // placeholders for the unused maps
+  if (q.epi2) {
+    if (p.bn_mask) { if (int e = make_nhwc_map(&tx[0], p.bn_mask, N, Hc, Wc, Nout, Nout, p.bw, p.bh, 1)) return e; }
+    if (p.bn_c) { if (int e = make_nhwc_map(&tx[1], p.bn_c, N, Hc, Wc, Nout, Nout, p.bw, p.bh, 1)) return e; }
+    if (p.res) { if (int e = make_nhwc_map(&tx[2], p.res, N, Hc, Wc, Nout, Nout, p.bw, p.bh, 1)) return e; }
+    if (int e = make_nhwc_map(&tx[3], p.out, N, Hc, Wc, Nout, Nout, p.bw, p.bh, 1)) return e;
+  }
+#define SVK_L3(K_, N_) if (KC == K_ && BN == N_) return dgrad ? launch3<K_, N_, true>(ta, tb, tx, q, smem, st) : launch3<K_, N_, false>(ta, tb, tx, q, smem, st)
   SVK_L3(32, 32); SVK_L3(32, 64); SVK_L3(64, 32); SVK_L3(64, 64);
 #undef SVK_L3
   svk_set_error("conv_tc3: no kernel for KC=%d BN=%d", KC, BN);

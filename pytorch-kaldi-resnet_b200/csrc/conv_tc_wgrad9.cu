@@ -31,6 +31,7 @@ struct Wgrad9P {
   int n_stages;
   float* ws;                   // [ksplit][9][C][C]
   long long ws_stride;
+  unsigned long long* prof;    // SVK_PROF=1 cycle counters (tc_common.cuh), else NULL
 };
 
 template <int CK>   // CK = C: 32 -> SWIZZLE_64B atoms, 64 -> SWIZZLE_128B atoms
@@ -75,20 +76,24 @@ conv_tc_wgrad9_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
   const int t_beg = ks * p.tiles_per;
   const int t_end = (t_beg + p.tiles_per) < p.num_tiles ? (t_beg + p.tiles_per) : p.num_tiles;
 
+  long long et0 = 0, ew = 0;     // SVK_PROF: epilogue timing
   if (warp == 0) {
     {   // the WHOLE warp runs this loop (uniform control flow); the issuing wrappers elect one lane
       int st = 0; uint32_t ph = 0;
+      const bool prof = p.prof != nullptr;
+      long long pw = 0; const long long pt0 = prof ? clock64() : 0;
       for (int tile = t_beg; tile < t_end; ++tile) {
         const int th = tile % p.tiles_h;
         const int n = tile / p.tiles_h;
         const int h0 = th * p.bh;
         const uint32_t sb = base + (uint32_t)st * p.stage_bytes;
-        mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+        mbar_wait_t(bar_empty + 8 * st, ph ^ 1u, prof, pw);
         mbar_expect_tx(bar_full + 8 * st, (uint32_t)(p.x_bytes + p.dy_bytes));
         tma_load_4d(sb, &tmX, bar_full + 8 * st, 0, -1, h0, n);
         tma_load_4d(sb + p.x_alloc, &tmDy, bar_full + 8 * st, 0, 0, h0 - 1, n);
         if (++st == p.n_stages) { st = 0; ph ^= 1u; }
       }
+      if (prof) prof_flush(p.prof, 4, clock64() - pt0, pw, lane);
     }
   } else if (warp == 1) {
     {   // the WHOLE warp runs this loop; one elected lane issues
@@ -96,8 +101,12 @@ conv_tc_wgrad9_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
       int st = 0; uint32_t ph = 0;
       const int ksteps = (p.bh * p.PW) / 16;
       const uint32_t lbo_a = (uint32_t)p.PW * ROWB;                 // dy atom a = rows shifted by a image rows (tap r = 2 - a)
+      const bool prof = p.prof != nullptr;
+      long long pwf = 0; const long long pt0 = prof ? clock64() : 0;
+      unsigned long long gt0 = 0;
+      if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
       for (int tile = t_beg; tile < t_end; ++tile) {
-        mbar_wait(bar_full + 8 * st, ph);
+        mbar_wait_t(bar_full + 8 * st, ph, prof, pwf);
         tc_fence_after();
         const uint32_t sb = base + (uint32_t)st * p.stage_bytes;
         uint64_t bd = make_desc(sb, ROWB, SBO, LAYOUT);              // x atom b = rows shifted by b pixels (tap s = b)
@@ -114,9 +123,19 @@ conv_tc_wgrad9_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
         if (++st == p.n_stages) { st = 0; ph ^= 1u; }
       }
       tc_commit(bar_done);
+      if (prof) {
+        mbar_wait(bar_done, 0);        // include the drain of the last MMAs
+        if (lane == 0) {
+          atomicAdd(p.prof + 0, 1ull); atomicAdd(p.prof + 1, (unsigned long long)(clock64() - pt0));
+          atomicAdd(p.prof + 2, (unsigned long long)pwf);
+          unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+          atomicAdd(p.prof + 8, gt1 - gt0); atomicMax(p.prof + 9, ~gt0); atomicMax(p.prof + 10, gt1);
+        }
+      }
     }
   } else {
-    mbar_wait(bar_done, 0);
+    et0 = p.prof ? clock64() : 0;
+    mbar_wait_t(bar_done, 0, p.prof != nullptr, ew);
     tc_fence_after();
     const int q = warp & 3;
     const int m = q * 32 + lane;                        // accumulator row = atom * CK + co
@@ -140,6 +159,7 @@ conv_tc_wgrad9_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
       }
     }
   }
+  if (p.prof && warp == 2) prof_flush(p.prof, 6, clock64() - et0, ew, lane);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -203,6 +223,7 @@ int svk_conv2d_wgrad9_tc(const svk_conv_desc* d, const void* x, const void* dy, 
   if (int e = plan9(d, &p, &smem)) return e;
   SVK_REQUIRE((size_t)p.ksplit * (size_t)p.ws_stride <= ws_floats, SVK_E_BADARG, "conv2d_wgrad9: workspace too small");
   p.ws = ws;
+  p.prof = svk_prof_buffer();
   const int C = d->Cin;
   CUtensorMap tdy, tx;
   if (int e = make_nhwc_map(&tdy, dy, d->N, d->Ho, d->Wo, C, C, p.PW, p.bh + 2, 1)) return e;

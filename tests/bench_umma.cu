@@ -43,8 +43,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)layout << 61;
   return d;
 }
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 template <int CG>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -187,6 +188,83 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int iters, int nst, i
   }
 }
 
+// Rate only (no result check): operand majors as in the wgrad kernels.  MN-major SW128 operands: atoms of 64 channels
+// (128-byte rows = K index), atom stride ATOM_B bytes (A) or B_LBO bytes (B: 128 = views one pixel apart, as wgrad9/wgradr).
+template <int N, int A_MN, int B_MN>
+__global__ void __launch_bounds__(128, 1) umma_rate_mn_kernel(int iters, int b_lbo, Result* res) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_ptr;
+  // A region: 32 KB at 0 ; B region: 64 KB at 32 KB.  Fill with small finite values.
+  for (int i = threadIdx.x; i < 98304 / 2; i += blockDim.x) reinterpret_cast<__nv_bfloat16*>(gbase)[i] = __float2bfloat16(0.5f);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_done)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_ptr;
+  bool ok = true;
+  long long c0 = 0, c1 = 0;
+  unsigned long long t0 = 0, t1 = 0;
+  if (warp == 0) {
+    constexpr uint32_t idesc = make_idesc(128, N, A_MN, B_MN);
+    // K-major: rows = M/N index, 128-byte rows, K advance = 32 B (4 steps per tile).
+    // MN-major: rows = K index (64 rows per tile), K advance = 16 rows = 2 KB (4 steps per tile).
+    const uint64_t a0 = A_MN ? make_desc(base, 8192, 1024, 2) : make_desc(base, 16, 1024, 2);
+    const uint64_t b0 = B_MN ? make_desc(base + 32768, (uint32_t)b_lbo, 1024, 2) : make_desc(base + 32768, 16, 1024, 2);
+    const uint64_t a_step = A_MN ? 128 : 2, b_step = B_MN ? 128 : 2;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    c0 = clock64();
+    uint32_t accum = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { tc_mma<1>(tmem_base, a0 + a_step * k, b0 + b_step * k, idesc, accum); accum = 1; }
+      }
+    }
+    tc_commit<1>(smem_u32(&bar_done));
+    ok = mbar_wait(smem_u32(&bar_done), 0);
+    c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { res[blockIdx.x].cycles = (unsigned long long)(c1 - c0); res[blockIdx.x].ns = t1 - t0; res[blockIdx.x].timeout = ok ? 0 : 1; }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+}
+
+template <int N, int A_MN, int B_MN>
+void run_mn(int grid, int iters, int b_lbo) {
+  const int smem = 98304 + 1024;
+  CK(cudaFuncSetAttribute(umma_rate_mn_kernel<N, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  Result* d; CK(cudaMalloc(&d, sizeof(Result) * grid)); CK(cudaMemset(d, 0, sizeof(Result) * grid));
+  for (int rep = 0; rep < 2; ++rep) {
+    umma_rate_mn_kernel<N, A_MN, B_MN><<<grid, 128, smem>>>(iters, b_lbo, d);
+    CK(cudaDeviceSynchronize());
+  }
+  std::vector<Result> h(grid); CK(cudaMemcpy(h.data(), d, sizeof(Result) * grid, cudaMemcpyDeviceToHost));
+  const double n_umma = (double)iters * 16;
+  double cyc = 0; int to = 0;
+  for (int i = 0; i < grid; ++i) { cyc += h[i].cycles; to += h[i].timeout; }
+  cyc /= grid;
+  printf("cta_group::1 M=128 N=%3d A %s B %s (B atom stride %5d B) : %7.1f cycles/UMMA  %6.1f MAC/clk/SM  timeout=%d\n", N,
+         A_MN ? "MN-major" : "K-major ", B_MN ? "MN-major" : "K-major ", b_lbo, cyc / n_umma, n_umma * 128.0 * N * 16.0 / cyc, to);
+  fflush(stdout);
+  CK(cudaFree(d));
+}
+
 template <int N, int CG>
 void run(int grid, int iters, int nst, int hammer) {
   const int stage = 128 * 128 + (N / CG) * 128;
@@ -225,6 +303,22 @@ int main(int argc, char** argv) {
   const int grid = sms & ~1;
   const int iters = argc > 1 ? atoi(argv[1]) : 512;
   printf("SMs %d, %d UMMAs per CTA per launch\n", sms, iters * 4 * 4);
+  if (argc > 2) {     // operand-major sweep
+    run_mn<128, 0, 0>(grid, iters, 16);
+    run_mn<128, 1, 0>(grid, iters, 16);
+    run_mn<128, 0, 1>(grid, iters, 8192);
+    run_mn<128, 1, 1>(grid, iters, 8192);
+    run_mn<128, 1, 1>(grid, iters, 128);
+    run_mn<192, 0, 0>(grid, iters, 16);
+    run_mn<192, 1, 0>(grid, iters, 16);
+    run_mn<192, 0, 1>(grid, iters, 8192);
+    run_mn<192, 1, 1>(grid, iters, 8192);
+    run_mn<192, 1, 1>(grid, iters, 128);
+    run_mn<256, 1, 1>(grid, iters, 8192);
+    run_mn<96, 1, 1>(grid, iters, 128);
+    run_mn<96, 0, 0>(grid, iters, 16);
+    return 0;
+  }
   for (int hammer = 0; hammer < 2; ++hammer) {
     run<32, 1>(grid, iters, 4, hammer);
     run<64, 1>(grid, iters, 4, hammer);

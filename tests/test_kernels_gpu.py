@@ -126,6 +126,23 @@ def test_conv_dgrad_bn_fusion(shape, impl, code):
                                  lib.BnBwdFuse(keep[0].data_ptr(), None, None, None, None), util.st())
 
 
+@pytest.mark.parametrize("env", [{"SVK_EPI2": "all"}, {"SVK_DISABLE_EPI2": "1"}, {"SVK_DISABLE_WGRAD9": "1", "SVK_DISABLE_WGRADR": "1"}],
+                         ids=["staged-epilogue-everywhere", "first-epilogue-only", "aligned-shift-wgrad"])
+def test_conv_kernel_variants(env):
+    """The library picks one kernel variant per shape (measured in the training step); the other variants stay selectable
+    through the environment for A/B runs.  The switches are read once per process, so the convolution tests are re-run in a
+    child process: every variant must meet the same parity bounds on every shape."""
+    if os.environ.get("SVK_VARIANT_CHILD"):
+        pytest.skip("child run")
+    child = dict(os.environ, SVK_VARIANT_CHILD="1", **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "test_conv_tcgen05_path or (test_conv_dgrad_bn_fusion and 1-1)",
+                        "-p", "no:cacheprovider"], env=child, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
 @pytest.mark.parametrize("impl,code", [(lib.IMPL_TCGEN05, lib.BF16), (lib.IMPL_SIMT, lib.F32)])
 @pytest.mark.parametrize("hw", [(40, 200, 32), (20, 100, 64), (10, 50, 128), (9, 27, 32)])
 def test_downsample_block_dgrad(hw, impl, code):
