@@ -230,6 +230,27 @@ int svk_topk_meanstd(const float* scores, int rows, int ncoh, int topk, float* m
 int svk_snorm_apply(const float* score, const int* ie, const int* it, const float* mean_e, const float* std_e,
                     const float* mean_t, const float* std_t, float* out, long long ntrials, void* stream);
 
+/* ---------------------------------------------------------------- scoring back end ------- */
+/* Stable ascending sort of (float64 key, int32 value) pairs (LSD radix, 8 x 8 bits; ties keep their input order).
+ * replaces: the stable `sorted(..., key=itemgetter(1))` over Python floats of compute_eer.py:38-40 and
+ * local/compute_min_dcf.py:58-61. */
+size_t svk_sort_pairs_f64_workspace_bytes(long long n);
+int svk_sort_pairs_f64(const double* keys, const int* vals, double* keys_out, int* vals_out, long long n,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* Labels (1 = target) in ascending score order -> out6 = { eer = max(fpr, fnr) at the first index minimising
+ * |fnr - fpr|, that index, min over i of c_miss*fnr*p_target + c_fa*fpr*(1-p_target) (not normalised), its first index,
+ * n_target, n_nontarget }, float64 with the reference's operation order.
+ * replaces: compute_eer.py:35-70,99-100; local/compute_min_dcf.py:54-106. */
+size_t svk_det_metrics_workspace_bytes(long long n);
+int svk_det_metrics(const int* sorted_labels, long long n, long long n_target, double p_target, double c_miss, double c_fa,
+                    double* out6, void* workspace, size_t workspace_bytes, void* stream);
+/* out[s] = mean of the rows X[order[offsets[s] .. offsets[s+1])], accumulated in that order (float32).
+ * replaces: compute_speaker_mean.py:16-27. */
+int svk_segment_mean(const float* X, const int* order, const int* offsets, int n_seg, int D, float* out, void* stream);
+/* out[d] = mean over the n rows of X[n, D] (float64 accumulation).  replaces: compute_mean.py:9-20. */
+size_t svk_col_mean_workspace_bytes(long long n, int D);
+int svk_col_mean(const float* X, long long n, int D, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -246,7 +246,93 @@ def scoring_case():
     print("wrote scoring: %d trials, score[0]=%.6f snorm[0]=%.6f" % (n_trials, scores[0], snorm[0]))
 
 
+def backend_case():
+    """Run the reference's compute_mean / compute_speaker_mean / compute_eer / local/compute_min_dcf on generated files."""
+    import compute_mean as ref_mean
+    import compute_speaker_mean as ref_spk
+    import compute_eer as ref_eer
+    sys.path.insert(0, os.path.join(os.path.dirname(REF), "local"))
+    import compute_min_dcf as ref_dcf
+    rs = np.random.RandomState(11)
+    D, n_utt, n_spk, n_trials = 48, 150, 23, 3000
+    emb = (rs.randn(n_utt, D) * 2 + 0.5).astype(np.float32)
+    spk_of = rs.randint(0, n_spk, n_utt)
+    utts = ["utt%04d" % i for i in range(n_utt)]
+    ie, it = rs.randint(0, n_utt, n_trials), rs.randint(0, n_utt, n_trials)
+    target = spk_of[ie] == spk_of[it]
+    # scores with ties (rounded to 2 decimals) so that the stable order of equal scores matters
+    sc = np.round(rs.randn(n_trials) + 1.5 * target, 2)
+    with tempfile.TemporaryDirectory() as d:
+        with open(d + "/emb.iv", "w") as f:
+            for k, v in zip(utts, emb):
+                f.write(k + " [ " + " ".join(map(str, v)) + " ]\n")
+        with open(d + "/utt2spk", "w") as f:
+            for k, s_ in zip(utts, spk_of):
+                f.write("%s spk%02d\n" % (k, s_))
+        seen = set()
+        with open(d + "/trials", "w") as ft, open(d + "/scores", "w") as fs:
+            keep = []
+            for t in range(n_trials):
+                key = (ie[t], it[t])
+                if key in seen:
+                    continue                      # the reference keys trials by the id pair: keep the pairs unique
+                seen.add(key)
+                keep.append(t)
+                ft.write("%s %s %s\n" % (utts[ie[t]], utts[it[t]], "target" if target[t] else "nontarget"))
+                fs.write("%s %s %s\n" % (utts[ie[t]], utts[it[t]], repr(float(sc[t]))))
+        keep = np.asarray(keep)
+        argv = sys.argv
+        out = {}
+        with contextlib.redirect_stdout(io.StringIO()):
+            sys.argv = ["compute_mean.py", d + "/emb.iv", d + "/mean.vec"]
+            ref_mean.main()
+            sys.argv = ["compute_speaker_mean.py", d + "/emb.iv", d + "/utt2spk", d + "/spk_mean.iv"]
+            ref_spk.main()
+        for name, mod, extra in (("eer", ref_eer, []), ("dcf_001", ref_dcf, ["--p-target", "0.01"]),
+                                 ("dcf_05", ref_dcf, ["--p-target", "0.05", "--c-miss", "2", "--c-fa", "1.5"])):
+            buf, err = io.StringIO(), io.StringIO()
+            with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(err):
+                sys.argv = [name] + extra + [d + "/scores", d + "/trials"]
+                mod.main()
+            out[name] = buf.getvalue().strip()
+            out[name + "_err"] = err.getvalue().strip().splitlines()[-1]
+        sys.argv = argv
+        files = {k: open(d + "/" + k).read() for k in ("emb.iv", "utt2spk", "trials", "scores", "mean.vec", "spk_mean.iv")}
+    # pin the oracle restatements on the same data
+    scores, labels = sc[keep], target[keep].astype(np.int64)
+    e, _ = O.eer(scores, labels)
+    assert "{0:.2%}".format(e) == out["eer"], (e, out["eer"])
+    # exact float64 equality with the reference's own functions
+    fn_r, fp_r, th_r = ref_eer.ComputeErrorRates(list(scores), list(labels))
+    fn_o, fp_o, th_o = O.error_rates(scores, labels)
+    assert np.array_equal(np.array(fn_r), fn_o) and np.array_equal(np.array(fp_r), fp_o) and np.array_equal(np.array(th_r), th_o)
+    for p_t, cm, cf, key in ((0.01, 1.0, 1.0, "dcf_001"), (0.05, 2.0, 1.5, "dcf_05")):
+        m_r, t_r = ref_dcf.ComputeMinDcf(fn_r, fp_r, th_r, p_t, cm, cf)
+        m_o, t_o = O.min_dcf(scores, labels, p_t, cm, cf)
+        assert m_r == m_o and t_r == t_o, (m_r, m_o, t_r, t_o)
+        assert "{0:.4f}".format(m_o) == out[key]
+    emb64 = np.array([[float(t) for t in map(str, v)] for v in emb], dtype=np.float64)
+    spk_names = sorted(set(spk_of), key=lambda s_: list(spk_of).index(s_))          # first-appearance order
+    remap = {s_: i for i, s_ in enumerate(spk_names)}
+    seg = np.array([remap[s_] for s_ in spk_of])
+    ref_spk_mean = np.array([[float(t) for t in l.split()[2:-1]] for l in files["spk_mean.iv"].splitlines()])
+    ref_mean_vec = np.array([float(t) for t in files["mean.vec"].split()[1:-1]])
+    assert np.array_equal(O.speaker_means(emb64, seg, len(spk_names)), ref_spk_mean.astype(np.float32)), "speaker means"   # str(float32) round-trips
+    assert np.allclose(O.global_mean(emb64), ref_mean_vec, rtol=0, atol=1e-7), "global mean"
+    np.savez_compressed(os.path.join(OUT, "backend.npz"), emb=emb, seg=seg, scores=scores, labels=labels,
+                        eer_out=np.array(out["eer"]), dcf001_out=np.array(out["dcf_001"]), dcf05_out=np.array(out["dcf_05"]),
+                        eer_value=np.float64(e), dcf001_value=np.float64(O.min_dcf(scores, labels, 0.01, 1.0, 1.0)[0]),
+                        dcf05_value=np.float64(O.min_dcf(scores, labels, 0.05, 2.0, 1.5)[0]),
+                        dcf05_err=np.array(out["dcf_05_err"]), spk_mean=ref_spk_mean, mean=ref_mean_vec,
+                        **{"file/" + k: np.array(v) for k, v in files.items()})
+    print("wrote backend: %d trials, eer %s, minDCF %s / %s" % (len(keep), out["eer"], out["dcf_001"], out["dcf_05"]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "backend":      # only the back-end fixture (the others stay as committed)
+        os.makedirs(OUT, exist_ok=True)
+        backend_case()
+        sys.exit(0)
     if not os.path.isdir(REF):
         sys.exit("the reference is not mounted at %s: fixtures can only be generated in the build container" % REF)
     os.makedirs(OUT, exist_ok=True)
@@ -256,3 +342,4 @@ if __name__ == "__main__":
     model_case("aamv1_f40", seed=3, spk_num=19, feat_dim=40, pooling="mean+std", loss="AAM-v1", B=6, T=40)
     kat_case()
     scoring_case()
+    backend_case()

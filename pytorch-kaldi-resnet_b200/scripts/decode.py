@@ -53,6 +53,10 @@ parser.add_argument('--out-path', type=str, required=True)
 parser.add_argument('--multiprocessing-distributed', action='store_true')
 parser.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
 parser.add_argument('--max-batch-frames', default=65536, type=int, help='frame budget of one padded batch')
+parser.add_argument('--embed-format', default='text', choices=['text', 'ark'],
+                    help="text: 'utt [ v0 ... ]' lines like the reference (decode.py:206); ark: Kaldi binary float vectors "
+                         "(kaldi_io.write_vec_flt) in <out-path>/<gpu>.ark — formatting / re-parsing 256 floats per utterance "
+                         "as text dominates the end-to-end scoring time at scale; every reader here accepts both")
 
 MAX_BATCH_UTTS = 64
 
@@ -159,10 +163,18 @@ def main_worker(gpu, ngpus_per_node, args):
     results = {}
     extract(model, dataset, mine, torch.device('cuda', dev_index), args.max_batch_frames,
             lambda utt, vec: results.__setitem__(utt, vec))
-    with open(os.path.join(args.out_path, name), 'w') as f:
-        for i in mine:                                   # scp order within the shard
-            utt = dataset.utts[i]
-            f.write(utt + ' [ ' + ' '.join(map(str, results[utt])) + ' ]\n')   # decode.py:206 format
+    if args.embed_format == 'ark':
+        import numpy as np
+        import kaldi_io
+        with open(os.path.join(args.out_path, name + '.ark'), 'wb') as f:
+            for i in mine:
+                utt = dataset.utts[i]
+                kaldi_io.write_vec_flt(f, np.asarray(results[utt], dtype=np.float32), key=utt)
+    else:
+        with open(os.path.join(args.out_path, name), 'w') as f:
+            for i in mine:                                   # scp order within the shard
+                utt = dataset.utts[i]
+                f.write(utt + ' [ ' + ' '.join(map(str, results[utt])) + ' ]\n')   # decode.py:206 format
     if args.distributed:
         dist.barrier()
         dist.destroy_process_group()

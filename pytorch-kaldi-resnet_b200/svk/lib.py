@@ -69,6 +69,10 @@ SIGNATURES = {
     "svk_cosine_score_pairs": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
     "svk_topk_meanstd": [_P, _I, _I, _I, _P, _P, _P],
     "svk_snorm_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _P],
+    "svk_sort_pairs_f64": [_P, _P, _P, _P, _L, _P, ctypes.c_size_t, _P],
+    "svk_det_metrics": [_P, _L, _L, c_double, c_double, c_double, _P, _P, ctypes.c_size_t, _P],
+    "svk_segment_mean": [_P, _P, _P, _I, _I, _P, _P],
+    "svk_col_mean": [_P, _L, _I, _P, _P, ctypes.c_size_t, _P],
 }
 
 _lib = None
@@ -94,6 +98,10 @@ def load():
     lib.svk_conv2d_wgrad_workspace_bytes.argtypes = [_D]
     lib.svk_gemm_tf32_workspace_bytes.restype = ctypes.c_size_t
     lib.svk_gemm_tf32_workspace_bytes.argtypes = [_I, _I, _I]
+    for name, argtypes in (("svk_sort_pairs_f64_workspace_bytes", [_L]), ("svk_det_metrics_workspace_bytes", [_L]),
+                           ("svk_col_mean_workspace_bytes", [_L, _I])):
+        getattr(lib, name).restype = ctypes.c_size_t
+        getattr(lib, name).argtypes = argtypes
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -4,10 +4,14 @@ replaces the per-trial / per-utterance Python loops of the reference:
     cosine_score.py:60-65            -> cosine_scores()          (svk_cosine_score_pairs)
     compute_topk_mean_std.py:10-23   -> cohort_topk_meanstd()    (svk_l2norm_rows_fwd + svk_sgemm + svk_topk_meanstd)
     adaptive_snorm.py:28-38          -> snorm_apply()            (svk_snorm_apply)
+    compute_mean.py:9-20             -> global_mean()            (svk_col_mean)
+    compute_speaker_mean.py:9-30     -> speaker_means()          (svk_segment_mean)
+    compute_eer.py:35-102, local/compute_min_dcf.py:54-120 -> det_metrics()  (svk_sort_pairs_f64 + svk_det_metrics)
 Embeddings are float32 on the device, exactly what the reference feeds torch (`torch.FloatTensor(vec - mean)`).
 """
 import torch
 
+from . import lib as _lib
 from .lib import call
 
 
@@ -88,3 +92,58 @@ def snorm_apply(scores, idx_enroll, idx_test, mean_e, std_e, mean_t, std_t, devi
     call.svk_snorm_apply(s.data_ptr(), ie.data_ptr(), it.data_ptr(), me.data_ptr(), se.data_ptr(), mt.data_ptr(),
                          sd.data_ptr(), out.data_ptr(), s.numel(), _st())
     return out
+
+
+def global_mean(vecs, device="cuda"):
+    """Mean over all rows (compute_mean.py:17).  Returns a float32 tensor [D]."""
+    X = _f32(vecs, device)
+    n, D = X.shape
+    out = torch.empty(D, dtype=torch.float32, device=device)
+    ws = torch.empty(_lib.load().svk_col_mean_workspace_bytes(n, D), dtype=torch.uint8, device=device)
+    call.svk_col_mean(X.data_ptr(), n, D, out.data_ptr(), ws.data_ptr(), ws.numel(), _st())
+    return out
+
+
+def speaker_means(vecs, seg_ids, n_seg, device="cuda"):
+    """Per-speaker mean of the rows of `vecs` (row r belongs to speaker seg_ids[r]), accumulated in row order like
+    compute_speaker_mean.py:16-27.  Returns a float32 tensor [n_seg, D]."""
+    import numpy as np
+    X = _f32(vecs, device)
+    seg = np.asarray(seg_ids, dtype=np.int64)
+    order = np.argsort(seg, kind="stable").astype(np.int32)              # rows grouped by speaker, file order inside
+    counts = np.bincount(seg, minlength=n_seg)
+    offsets = np.zeros(n_seg + 1, dtype=np.int32)
+    np.cumsum(counts, out=offsets[1:])
+    out = torch.empty(n_seg, X.shape[1], dtype=torch.float32, device=device)
+    order_d, offsets_d = _i32(order, device), _i32(offsets, device)       # keep them alive across the launch
+    call.svk_segment_mean(X.data_ptr(), order_d.data_ptr(), offsets_d.data_ptr(), n_seg, X.shape[1], out.data_ptr(), _st())
+    return out
+
+
+def sort_pairs(keys, vals, device="cuda"):
+    """Stable ascending sort of float64 keys with int32 payloads on the device."""
+    k = torch.as_tensor(keys, dtype=torch.float64, device=device).contiguous()
+    v = _i32(vals, device)
+    n = k.numel()
+    ko, vo = torch.empty_like(k), torch.empty_like(v)
+    ws = torch.empty(_lib.load().svk_sort_pairs_f64_workspace_bytes(n), dtype=torch.uint8, device=device)
+    call.svk_sort_pairs_f64(k.data_ptr(), v.data_ptr(), ko.data_ptr(), vo.data_ptr(), n, ws.data_ptr(), ws.numel(), _st())
+    return ko, vo
+
+
+def det_metrics(scores, labels, p_target=0.01, c_miss=1.0, c_fa=1.0, device="cuda"):
+    """EER and minDCF of a scored trial list (labels: 1 = target, 0 = non-target), computed like the reference:
+    stable ascending sort of the float64 scores, thresholds = sorted scores, fnr / fpr from cumulative counts.
+    Returns dict(eer, eer_index, min_dcf, min_dcf_threshold, n_target, n_nontarget)."""
+    import numpy as np
+    lab = np.asarray(labels, dtype=np.int32)
+    n, n_t = lab.size, int(lab.sum())
+    ks, ls = sort_pairs(scores, lab, device)
+    out = torch.empty(6, dtype=torch.float64, device=device)
+    ws = torch.empty(_lib.load().svk_det_metrics_workspace_bytes(n), dtype=torch.uint8, device=device)
+    call.svk_det_metrics(ls.data_ptr(), n, n_t, float(p_target), float(c_miss), float(c_fa), out.data_ptr(), ws.data_ptr(),
+                         ws.numel(), _st())
+    o = out.cpu().numpy()
+    c_def = min(c_miss * p_target, c_fa * (1 - p_target))                # compute_min_dcf.py:104
+    return {"eer": float(o[0]), "eer_index": int(o[1]), "min_dcf": float(o[2]) / c_def,
+            "min_dcf_threshold": float(ks[int(o[3])].item()), "n_target": int(o[4]), "n_nontarget": int(o[5])}

@@ -245,6 +245,71 @@ __global__ void __launch_bounds__(128, 1) umma_rate_mn_kernel(int iters, int b_l
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
 }
 
+// K-major SWIZZLE_64B operands (32-channel layers: 64-byte rows): 2 K steps per tile row.
+template <int N>
+__global__ void __launch_bounds__(128, 1) umma_rate_sw64_kernel(int iters, Result* res) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_ptr;
+  for (int i = threadIdx.x; i < 98304 / 2; i += blockDim.x) reinterpret_cast<__nv_bfloat16*>(gbase)[i] = __float2bfloat16(0.5f);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_done)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_ptr;
+  bool ok = true;
+  long long c0 = 0, c1 = 0;
+  if (warp == 0) {
+    constexpr uint32_t idesc = make_idesc(128, N);
+    c0 = clock64();
+    uint32_t accum = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {          // 8 "stages" of 128 rows x 64 B (8 KB each), B behind at +64 KB
+        const uint64_t a0 = make_desc(base + s * 8192, 16, 512, 4);
+        const uint64_t b0 = make_desc(base + 65536 + s * 4096, 16, 512, 4);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { tc_mma<1>(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc, accum); accum = 1; }
+      }
+    }
+    tc_commit<1>(smem_u32(&bar_done));
+    ok = mbar_wait(smem_u32(&bar_done), 0);
+    c1 = clock64();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { res[blockIdx.x].cycles = (unsigned long long)(c1 - c0); res[blockIdx.x].timeout = ok ? 0 : 1; }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+}
+template <int N>
+void run_sw64(int grid, int iters) {
+  const int smem = 98304 + 1024;
+  CK(cudaFuncSetAttribute(umma_rate_sw64_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  Result* d; CK(cudaMalloc(&d, sizeof(Result) * grid)); CK(cudaMemset(d, 0, sizeof(Result) * grid));
+  for (int rep = 0; rep < 2; ++rep) { umma_rate_sw64_kernel<N><<<grid, 128, smem>>>(iters, d); CK(cudaDeviceSynchronize()); }
+  std::vector<Result> h(grid); CK(cudaMemcpy(h.data(), d, sizeof(Result) * grid, cudaMemcpyDeviceToHost));
+  double cyc = 0; int to = 0;
+  for (int i = 0; i < grid; ++i) { cyc += h[i].cycles; to += h[i].timeout; }
+  cyc /= grid;
+  const double n_umma = (double)iters * 16;
+  printf("cta_group::1 M=128 N=%3d K-major SWIZZLE_64B (64-byte rows) : %7.1f cycles/UMMA  %6.1f MAC/clk/SM  timeout=%d\n", N,
+         cyc / n_umma, n_umma * 128.0 * N * 16.0 / cyc, to);
+  fflush(stdout);
+  CK(cudaFree(d));
+}
+
 template <int N, int A_MN, int B_MN>
 void run_mn(int grid, int iters, int b_lbo) {
   const int smem = 98304 + 1024;
@@ -317,6 +382,11 @@ int main(int argc, char** argv) {
     run_mn<256, 1, 1>(grid, iters, 8192);
     run_mn<96, 1, 1>(grid, iters, 128);
     run_mn<96, 0, 0>(grid, iters, 16);
+    run_mn<32, 0, 0>(grid, iters, 16);
+    run_mn<64, 0, 0>(grid, iters, 16);
+    run_sw64<32>(grid, iters);
+    run_sw64<64>(grid, iters);
+    run_sw64<128>(grid, iters);
     return 0;
   }
   for (int hammer = 0; hammer < 2; ++hammer) {

@@ -438,6 +438,83 @@ def test_scoring_kernels_match_reference_scripts():
     assert scoring.cosine_scores(e32, e32, None, np.zeros(0, np.int32), np.zeros(0, np.int32)).numel() == 0
 
 
+def test_backend_kernels_match_reference_scripts():
+    """Radix sort, detection metrics and mean kernels against the reference scripts' outputs."""
+    from svk import scoring
+    fx = np.load(os.path.join(util.ROOT, "tests", "golden", "backend.npz"))
+    scores, labels = fx["scores"], fx["labels"]
+    r = scoring.det_metrics(scores, labels, 0.01, 1.0, 1.0)
+    assert r["eer"] == float(fx["eer_value"]) and "{0:.2%}".format(r["eer"]) == str(fx["eer_out"])          # bit-exact float64
+    assert r["min_dcf"] == float(fx["dcf001_value"])
+    r2 = scoring.det_metrics(scores, labels, 0.05, 2.0, 1.5)
+    assert r2["min_dcf"] == float(fx["dcf05_value"]) and "{0:.4f}".format(r2["min_dcf"]) == str(fx["dcf05_out"])
+    assert r2["min_dcf_threshold"] == O.min_dcf(scores, labels, 0.05, 2.0, 1.5)[1]
+    assert r["n_target"] == int(labels.sum()) and r["n_nontarget"] == int((1 - labels).sum())
+    # the sort itself: stable, float64 keys, negative / zero / denormal / tied values, sizes around the 2,048-key chunk
+    g = np.random.RandomState(3)
+    for n in (1, 2, 255, 2048, 2049, 100003):
+        k = np.round(g.randn(n) * 3, 1 if n > 1000 else 3)
+        k[g.randint(0, n, max(1, n // 50))] = 0.0
+        k[g.randint(0, n, max(1, n // 50))] = -0.0
+        k[g.randint(0, n, max(1, n // 100))] = 5e-324
+        v = np.arange(n, dtype=np.int32)
+        ks, vs = scoring.sort_pairs(k, v)
+        order = np.argsort(k, kind="stable")
+        assert np.array_equal(vs.cpu().numpy()[k[order] != 0], v[order][k[order] != 0])      # (+0.0 / -0.0 compare equal:
+        assert np.array_equal(ks.cpu().numpy(), k[order])                                      #  their relative order is free)
+    # properties at a size the Python reference would take minutes for: 1 M trials
+    n = 1 << 20
+    lab = (g.rand(n) < 0.3).astype(np.int32)
+    sc = g.randn(n) + 2.0 * lab
+    big = scoring.det_metrics(sc, lab)
+    e_ref, _ = O.eer(sc, lab)
+    m_ref, t_ref = O.min_dcf(sc, lab)
+    assert big["eer"] == e_ref and big["min_dcf"] == m_ref and big["min_dcf_threshold"] == t_ref
+    # means
+    emb64 = np.array([[float(t) for t in map(str, v)] for v in fx["emb"]], dtype=np.float64)
+    e32 = emb64.astype(np.float32)
+    n_seg = int(fx["seg"].max()) + 1
+    sm = scoring.speaker_means(e32, fx["seg"], n_seg).cpu().numpy()
+    assert np.abs(sm - fx["spk_mean"]).max() <= 1e-6
+    gm = scoring.global_mean(e32).cpu().numpy()
+    assert np.abs(gm - fx["mean"]).max() <= 1e-6
+
+
+def test_backend_scripts_end_to_end_on_reference_files():
+    """compute_mean.py / compute_speaker_mean.py / compute_eer.py / compute_min_dcf.py drop-ins on the reference's files:
+    same command lines, same output text (text embeddings and a binary-vector ark give the same means)."""
+    import kaldi_io
+    fx = np.load(os.path.join(util.ROOT, "tests", "golden", "backend.npz"))
+    scripts = os.path.join(util.PKG, "scripts")
+    with tempfile.TemporaryDirectory() as d:
+        for k in ("emb.iv", "utt2spk", "trials", "scores"):
+            open(os.path.join(d, k), "w").write(str(fx["file/" + k]))
+        run = lambda *a: subprocess.run([sys.executable] + list(a), check=True, capture_output=True, text=True, cwd=d)
+        assert run(os.path.join(scripts, "compute_eer.py"), "scores", "trials").stdout.strip() == str(fx["eer_out"])
+        assert run(os.path.join(scripts, "compute_min_dcf.py"), "--p-target", "0.01", "scores", "trials").stdout.strip() == str(fx["dcf001_out"])
+        r = run(os.path.join(scripts, "compute_min_dcf.py"), "--p-target", "0.05", "--c-miss", "2", "--c-fa", "1.5", "scores", "trials")
+        assert r.stdout.strip() == str(fx["dcf05_out"])
+        assert r.stderr.strip().splitlines()[-1] == str(fx["dcf05_err"])
+        run(os.path.join(scripts, "compute_speaker_mean.py"), "emb.iv", "utt2spk", "spk_mean.iv")
+        ref_lines = str(fx["file/spk_mean.iv"]).splitlines()
+        got_lines = open(os.path.join(d, "spk_mean.iv")).read().splitlines()
+        assert [l.split()[0] for l in got_lines] == [l.split()[0] for l in ref_lines]          # same speakers, same order
+        got = np.array([[float(t) for t in l.split()[2:-1]] for l in got_lines])
+        assert np.abs(got - fx["spk_mean"]).max() <= 1e-6
+        run(os.path.join(scripts, "compute_mean.py"), "emb.iv", "mean.vec")
+        txt = open(os.path.join(d, "mean.vec")).read()
+        assert txt.startswith(" [ ") and txt.endswith(" ]\n")
+        assert np.abs(np.array([float(t) for t in txt.split()[1:-1]]) - fx["mean"]).max() <= 1e-6
+        # binary fast path: the same embeddings as a Kaldi binary float-vector ark
+        keys = [l.split()[0] for l in str(fx["file/emb.iv"]).splitlines()]
+        with open(os.path.join(d, "emb.ark"), "wb") as f:
+            for k, v in zip(keys, fx["emb"]):
+                kaldi_io.write_vec_flt(f, np.asarray(v, np.float32), key=k)
+        run(os.path.join(scripts, "compute_mean.py"), "emb.ark", "mean_b.vec")
+        tb = open(os.path.join(d, "mean_b.vec")).read()
+        assert np.abs(np.array([float(t) for t in tb.split()[1:-1]]) - fx["mean"]).max() <= 1e-6
+
+
 def test_scoring_scripts_end_to_end_on_reference_files():
     """The CLI drop-ins read the files the reference's own scripts read and reproduce their output files."""
     fx = np.load(os.path.join(util.ROOT, "tests", "golden", "scoring.npz"))
@@ -492,7 +569,15 @@ def test_decode_script_matches_batch1_oracle():
                         "--out-path", os.path.join(d, "emb"), "--gpu", "0", "--max-batch-frames", "200"],
                        check=True, capture_output=True)
         got = dict(kaldi_io.read_vec_flt_ark(os.path.join(d, "emb", "0")))
-    assert sorted(got) == sorted(mats)
+        # binary fast path: same embeddings as Kaldi float-vector ark, bit-identical to the text ones
+        subprocess.run([sys.executable, os.path.join(util.PKG, "scripts", "decode.py"), "--spk_num", "12", "--input-dim", "40",
+                        "--pooling", "mean+std", "--model-path", os.path.join(d, "ckpt.pth.tar"), "--decode-scp", scp,
+                        "--out-path", os.path.join(d, "emb"), "--gpu", "0", "--max-batch-frames", "200", "--embed-format", "ark"],
+                       check=True, capture_output=True)
+        got_b = dict(kaldi_io.read_vec_flt_ark(os.path.join(d, "emb", "0.ark")))
+    assert sorted(got) == sorted(mats) and sorted(got_b) == sorted(mats)
+    for key in mats:
+        assert got_b[key].dtype == np.float32 and np.array_equal(got_b[key], got[key].astype(np.float32))
     for key, mat in mats.items():
         with torch.no_grad():
             ref = O.embed(sd, torch.from_numpy(mat.T.copy()).unsqueeze(0), "mean+std", train=False)[0]

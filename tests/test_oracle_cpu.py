@@ -127,6 +127,26 @@ def test_oracle_scoring_matches_reference_scripts():
     assert np.abs(sn - fx["snorm"]).max() <= 1e-9
 
 
+def test_oracle_backend_matches_reference_scripts():
+    """EER / minDCF / speaker means restated in numpy against the outputs of the reference's compute_eer.py,
+    local/compute_min_dcf.py, compute_speaker_mean.py and compute_mean.py (fixture: oracle/make_golden.py backend)."""
+    fx = np.load(os.path.join(U.GOLDEN, "backend.npz"))
+    scores, labels = fx["scores"], fx["labels"]
+    e, idx = O.eer(scores, labels)
+    assert "{0:.2%}".format(e) == str(fx["eer_out"]) and e == float(fx["eer_value"])
+    m1, _ = O.min_dcf(scores, labels, 0.01, 1.0, 1.0)
+    m2, _ = O.min_dcf(scores, labels, 0.05, 2.0, 1.5)
+    assert "{0:.4f}".format(m1) == str(fx["dcf001_out"]) and m1 == float(fx["dcf001_value"])
+    assert "{0:.4f}".format(m2) == str(fx["dcf05_out"]) and m2 == float(fx["dcf05_value"])
+    # ties: equal scores keep their file order (stable sort) — a permutation inside a tie group changes the curve
+    fn, fp, thr = O.error_rates([0.5, 0.5, 0.1, 0.9], [1, 0, 0, 1])
+    assert list(thr) == [0.1, 0.5, 0.5, 0.9] and list(fn) == [0.0, 0.5, 0.5, 1.0] and list(fp) == [0.5, 0.5, 0.0, 0.0]
+    emb64 = np.array([[float(t) for t in map(str, v)] for v in fx["emb"]], dtype=np.float64)
+    n_seg = int(fx["seg"].max()) + 1
+    assert np.array_equal(O.speaker_means(emb64, fx["seg"], n_seg), fx["spk_mean"].astype(np.float32))
+    assert np.abs(O.global_mean(emb64) - fx["mean"]).max() <= 1e-7
+
+
 def test_storage_rounding_emulation_matches_measured_bf16_drift():
     """rounding every stored tensor to bf16 (fp32 math) makes layer4 drift by several percent on a
     random-init network — the reason the bf16 end-to-end test is layer-local."""
