@@ -59,6 +59,16 @@ parser.add_argument('--embed-format', default='text', choices=['text', 'ark'],
                          "as text dominates the end-to-end scoring time at scale; every reader here accepts both")
 
 MAX_BATCH_UTTS = 64
+STAGE_SLOTS = int(os.environ.get("SVK_STAGE_SLOTS", "3"))   # pinned staging slots (= batches in flight on the host side)
+_PINNED = {}             # (slot, kind) -> pinned tensor, grown on demand and kept across extract() calls
+
+
+def _pinned(slot, kind, numel, dtype):
+    t = _PINNED.get((slot, kind))
+    if t is None or t.numel() < numel or t.dtype != dtype:
+        t = torch.empty(numel, dtype=dtype).pin_memory()
+        _PINNED[(slot, kind)] = t
+    return t
 
 
 def main():
@@ -99,33 +109,60 @@ def extract(model, dataset, indices, device, max_frames, on_result):
     lengths = [dataset.num_frames(i) if dataset.seq_len < 0 else dataset.seq_len for i in range(len(dataset))]
     batches = plan_batches(lengths, indices, max_frames)
     feat_dim = model.feat_dim
+    if not batches:
+        return
     copy_stream = torch.cuda.Stream(device=device)
+    # Persistent pinned staging slots, sized for the largest padded batch (cudaHostAlloc per batch cost more than the batch's
+    # forward pass), filled by a small thread pool a few batches ahead: reading / padding 64 utterances in Python takes
+    # longer than their forward pass, and the numpy / torch copies release the GIL.
+    from concurrent.futures import ThreadPoolExecutor
+    nslot = min(STAGE_SLOTS, len(batches))
+    cap = max(len(b) * max(lengths[i] for i in b) for b in batches) * feat_dim
+    pinned = [_pinned(k, "x", cap, torch.float32) for k in range(nslot)]
+    pinned_len = [_pinned(k, "len", MAX_BATCH_UTTS, torch.int32) for k in range(nslot)]
 
-    def stage(batch):
+    def fill(slot, batch):                                       # host side only: no CUDA calls on the worker threads
         mats = [dataset[i][0] for i in batch]                    # (F, T_i) float32
-        tmax = max(m.shape[1] for m in mats)
-        host = torch.zeros(len(mats), feat_dim, tmax, dtype=torch.float32).pin_memory()
+        lens = [m.shape[1] for m in mats]
+        tmax = max(lens)
+        host = pinned[slot][:len(mats) * feat_dim * tmax].view(len(mats), feat_dim, tmax)
+        same = min(lens) == tmax
+        if not same:
+            host.zero_()
         for r, m in enumerate(mats):
             host[r, :, :m.shape[1]] = torch.from_numpy(np.ascontiguousarray(m))
-        lens = torch.tensor([m.shape[1] for m in mats], dtype=torch.int32).pin_memory()
-        with torch.cuda.stream(copy_stream):
-            x = host.to(device, non_blocking=True)
-            ln = lens.to(device, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return x, ln, ev, host, lens
+        hl = pinned_len[slot][:len(mats)]
+        hl.copy_(torch.tensor(lens, dtype=torch.int32))
+        return host, hl, same
 
-    nxt = stage(batches[0]) if batches else None
-    with torch.no_grad():
-        for bi, batch in enumerate(batches):
-            x, ln, ev, _h, _l = nxt
-            nxt = stage(batches[bi + 1]) if bi + 1 < len(batches) else None   # overlap the next copy with this batch
-            torch.cuda.current_stream().wait_event(ev)
-            same = bool((ln == ln[0]).all().item()) if len(batch) > 1 else True
-            emb = model.predict(x, lengths=None if same else ln)
-            out = emb.float().cpu().numpy()
-            for r, i in enumerate(batch):
-                on_result(dataset.utts[i], out[r])
+    def collect(batch, emb):
+        out = emb.float().cpu().numpy()                          # waits for that batch's kernels
+        for r, i in enumerate(batch):
+            on_result(dataset.utts[i], out[r])
+
+    pool = ThreadPoolExecutor(max_workers=max(1, nslot - 1))
+    try:
+        futures = {j: pool.submit(fill, j % nslot, batches[j]) for j in range(nslot)}
+        pending = None
+        with torch.no_grad():
+            for bi, batch in enumerate(batches):
+                host, hl, same = futures.pop(bi).result()
+                with torch.cuda.stream(copy_stream):
+                    x = host.to(device, non_blocking=True)
+                    ln = hl.to(device, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                torch.cuda.current_stream().wait_event(ev)
+                if pending is not None:
+                    collect(*pending)                             # batch bi-1 is done: its result is read back and its
+                    j = bi - 1 + nslot                            # pinned slot (copied out before its kernels ran) is refilled
+                    if j < len(batches):
+                        futures[j] = pool.submit(fill, j % nslot, batches[j])
+                emb = model.predict(x, lengths=None if same else ln)   # asynchronous launches
+                pending = (batch, emb)
+            collect(*pending)
+    finally:
+        pool.shutdown(wait=True)
 
 
 def main_worker(gpu, ngpus_per_node, args):
