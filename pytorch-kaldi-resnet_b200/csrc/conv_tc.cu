@@ -163,6 +163,200 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------ fprop / dgrad, CTA pair
+// Same dataflow on a pair of CTAs (cluster of 2, tcgen05 cta_group::2): each CTA loads ITS pixel tile (A, 128 rows) and
+// HALF of the filter block (B, BN/2 rows); the leader CTA issues M = 256 x N = BN x K = 16 instructions that read both
+// CTAs' shared memory and write 128 accumulator rows into each CTA's TMEM.  The tensor pipe gains nothing from this
+// (tests/bench_umma.cu: cta_group::1 already runs N >= 128 tiles at the full rate) — the point is shared-memory INGEST: the
+// late stages wait for operands 44-46 % of their MMA loop at ~56 B/clk/SM (profiles/r01b_what_bounds_the_convs.md), and a
+// pair moves 25 % fewer bytes per MAC (A + B/2 instead of A + B per tile).  Epilogues are the single-CTA ones: every CTA
+// drains its own accumulator rows and signals the leader's accumulator-free barrier (GatherP::pair).
+//   full[s]   (each CTA): its own producer's arrive.expect_tx + the bytes of its own TMA loads
+//   pfull[s]  (leader):   "the peer's stage s has landed" — relayed by the peer's (otherwise idle) MMA warp, ONE remote arrive
+//                         per stage (TMA loads that signal the leader's barrier directly, cp.async.bulk .cta_group::2, ran 1.85x
+//                         slower than the single-CTA kernel: every packet of the peer's loads sends a remote complete_tx)
+//   empty[s]  (each CTA): multicast tcgen05.commit of the leader when the MMAs that read stage s have completed
+//   tfull[a]  (each CTA): multicast commit after the last MMA of a tile pair
+//   tempty[a] (leader):   one arrive per epilogue warp of BOTH CTAs
+template <int KC, int BN>
+struct Gather2Cfg {
+  static constexpr int ROWB = KC * 2;
+  static constexpr int A_BYTES = 128 * ROWB;
+  static constexpr int B_BYTES = (BN / 2) * ROWB;            // this CTA's half of the filter block
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (180 * 1024) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM = STAGES * STAGE + SMEM_AUX + SCR_BYTES + COEF_BYTES + 1024;
+  static constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
+  static constexpr uint32_t SBO = 8 * ROWB;
+};
+
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  if (elect_one()) asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  if (elect_one()) asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {      // arrives on `bar` of BOTH CTAs of the pair
+  if (elect_one()) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int KC, int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SVK_GATHER_BOUNDS(BN), 1)
+conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ GatherP p) {
+  typedef Gather2Cfg<KC, BN> Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t stage0 = base;
+  const uint32_t aux = base + Cfg::STAGES * Cfg::STAGE;
+  const uint32_t bar_full = aux, bar_empty = aux + 64, bar_tfull = aux + 128, bar_tempty = aux + 144, bar_pfull = aux + 192;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + Cfg::STAGES * Cfg::STAGE + 160);
+  float* scr = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE + SMEM_AUX);
+  float* coef = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE + SMEM_AUX + SCR_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the MMAs)
+  const int n_epi_warps = ((int)blockDim.x - 64) >> 5;     // 4 or 8; every one of them drains every tile it is scheduled on
+
+  // arrivals that free an accumulator buffer: the epilogue warps of BOTH CTAs that drain it
+  const uint32_t per_cta = (p.bn_mask && BN >= 128 && blockDim.x == GATHER_THREADS) ? 8u : 4u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_pfull + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * per_cta); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  (void)n_epi_warps;
+  if (p.scale) {
+    for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
+  }
+  if (p.bn_c) {
+    for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.bn_mean[i]; coef[512 + i] = p.bn_rstd[i]; }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // both CTAs' barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int ksteps = p.ntaps * p.kchunks;
+  const int n_pairs = (p.total_tiles + 1) >> 1;             // n_blocks == 1: tile = pixel tile; pair k = tiles (2k, 2k+1)
+  const int pair0 = (int)(blockIdx.x >> 1), pair_step = (int)(gridDim.x >> 1);
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0; uint32_t ph = 0;
+    const uint32_t a_bytes = (uint32_t)(p.bh * p.bw) * Cfg::ROWB;
+    const bool prof = p.prof != nullptr;
+    long long pw = 0; const long long pt0 = prof ? clock64() : 0;
+    for (int k = pair0; k < n_pairs; k += pair_step) {
+      int tile = 2 * k + (int)rank;
+      if (tile >= p.total_tiles) tile = 2 * k;              // odd tile count: the last pair's second tile is a duplicate (never stored)
+      int pt = tile;
+      const int tw = pt % p.tiles_w; pt /= p.tiles_w;
+      const int th = pt % p.tiles_h;
+      const int n = pt / p.tiles_h;
+      const int h0 = th * p.bh * p.in_mul, w0 = tw * p.bw * p.in_mul;
+      for (int t = 0; t < p.ntaps; ++t) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait_t(bar_empty + 8 * stage, ph ^ 1u, prof, pw);
+          const uint32_t sa = stage0 + stage * Cfg::STAGE;
+          mbar_expect_tx(bar_full + 8 * stage, a_bytes + (uint32_t)Cfg::B_BYTES);
+          tma_load_4d(sa, &tmA, bar_full + 8 * stage, kc * KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full + 8 * stage, kc * KC, p.tap_w[t] * p.Nout + (int)rank * (BN / 2));
+          if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; }
+        }
+      }
+    }
+    if (prof && rank == 0) prof_flush(p.prof, 4, clock64() - pt0, pw, lane);
+    if (prof && rank == 1 && lane == 0) atomicAdd(p.prof + 14, (unsigned long long)pw);      // peer producer: waiting for a free slot
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(256, BN, 0, 0);
+      int stage = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t aph = 0;
+      const uint64_t a_desc0 = make_desc(stage0, 16, Cfg::SBO, Cfg::LAYOUT);
+      uint64_t a_desc = a_desc0;
+      const bool prof = p.prof != nullptr;
+      long long pwf = 0, pwp = 0, pwt = 0; const long long pt0 = prof ? clock64() : 0;
+      for (int k = pair0; k < n_pairs; k += pair_step) {
+        mbar_wait_t(bar_tempty + 8 * acc, aph ^ 1u, prof, pwt);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait_t(bar_full + 8 * stage, ph, prof, pwf);
+          { const long long t0 = prof ? clock64() : 0;
+            mbar_wait(bar_pfull + 8 * stage, ph);              // the peer's half of this stage has landed too
+            if (prof) pwp += clock64() - t0; }
+          tc_fence_after();
+          const uint64_t b_desc = a_desc + (uint64_t)(Cfg::A_BYTES >> 4);
+          tc_mma_pair(d_tmem, a_desc, b_desc, idesc, ks != 0 ? 1u : 0u);
+#pragma unroll
+          for (int kk = 1; kk < KC / 16; ++kk) tc_mma_pair(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, 1u);
+          tc_commit_pair(bar_empty + 8 * stage);
+          a_desc += (uint64_t)(Cfg::STAGE >> 4);
+          if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; a_desc = a_desc0; }
+        }
+        tc_commit_pair(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
+      }
+      if (prof && lane == 0) {
+        atomicAdd(p.prof + 0, 1ull); atomicAdd(p.prof + 1, (unsigned long long)(clock64() - pt0));
+        atomicAdd(p.prof + 2, (unsigned long long)pwf); atomicAdd(p.prof + 3, (unsigned long long)pwt);
+        atomicAdd(p.prof + 13, (unsigned long long)pwp);
+      }
+    } else {
+      // peer CTA: relay "stage landed" to the leader, one remote arrive per stage
+      int stage = 0; uint32_t ph = 0;
+      const bool prof = p.prof != nullptr;
+      long long pwr = 0;
+      for (int k = pair0; k < n_pairs; k += pair_step) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait_t(bar_full + 8 * stage, ph, prof, pwr);
+          if (elect_one()) mbar_arrive_cluster(mapa_u32(bar_pfull + 8 * stage, 0));
+          __syncwarp();
+          if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; }
+        }
+      }
+      if (prof && lane == 0) atomicAdd(p.prof + 15, (unsigned long long)pwr);                  // peer relay: waiting for its own loads
+    }
+  } else {
+    // the single-CTA epilogues: tile = blockIdx.x + j * gridDim.x = 2 * pair + rank
+    if (p.bn_mask) {
+      if (BN >= 128 && blockDim.x == GATHER_THREADS)
+        gather_epilogue_bn<BN, (BN >= 128)>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
+      else
+        gather_epilogue_bn<BN, false>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
+    }
+    else gather_epilogue<BN>(p, tmem_base, bar_tfull, bar_tempty, scr, coef, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // no CTA leaves while its pair may still signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------ wgrad kernel
 struct WgradP {
   int bh, bw, P;              // pixel tile; P = bh*bw (multiple of 16) = K extent of one tile
@@ -366,6 +560,49 @@ int launch_gather_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP&
   SVK_LAUNCH_CHECK("conv_tc_gather");
   return 0;
 }
+template <int KC, int BN>
+int launch_gather2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP& p, cudaStream_t st) {
+  typedef Gather2Cfg<KC, BN> Cfg;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_gather2_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int n_pairs = (p.total_tiles + 1) / 2;
+  const int threads = p.bn_mask ? GATHER_THREADS : TC_THREADS;
+  // a pair needs two SMs of one TPC: ask the driver how many pairs can be resident at once (fewer than SMs / 2 when TPCs
+  // have a single enabled SM) — a persistent grid larger than that runs in two waves
+  static int max_pairs[2] = {0, 0};
+  int& mp = max_pairs[p.bn_mask ? 1 : 0];
+  if (mp == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(svk_num_sms() & ~1); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = Cfg::SMEM;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, conv_tc_gather2_kernel<KC, BN>, &cfg);
+    if (e != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = svk_num_sms() / 2; }
+    mp = nc;
+    if (getenv("SVK_VERBOSE")) fprintf(stderr, "svk: conv_tc_gather2<%d,%d> threads %d: %d resident CTA pairs\n", KC, BN, threads, nc);
+  }
+  const int grid = 2 * (n_pairs < mp ? n_pairs : mp);
+  conv_tc_gather2_kernel<KC, BN><<<grid, threads, Cfg::SMEM, st>>>(ta, tb, p);
+  SVK_LAUNCH_CHECK("conv_tc_gather2");
+  return 0;
+}
+// CTA-pair variant: one N block of 128 / 256 channels, 64-channel K chunks, at least one pair of tiles.  OFF by default:
+// measured equal to the single-CTA kernel (stage 3 fprop / dgrad 62.9 / 51.0 us vs 58.8 / 48.1; stage 4 47.7 / 35.9 vs
+// 46.4 / 36.3): it removes most of the operand waiting (32 k -> 23 k cycles per CTA) but a cta_group::2 instruction then
+// takes ~103 cycles instead of ~79 next to the TMA writes — the late stages are bound by shared-memory bandwidth (UMMA
+// operand reads + TMA writes of operands that are used once), not by the L2 -> SM path.  SVK_ENABLE_PAIR=1 selects it.
+bool gather2_applicable(int KC, int BN, const GatherP& p) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SVK_ENABLE_PAIR"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on && KC == 64 && (BN == 128 || BN == 256) && p.n_blocks == 1 && p.total_tiles >= 2 && !p.dbg;
+}
+
 int launch_gather(int KC, int BN, const CUtensorMap& ta, const CUtensorMap& tb, const GatherP& p, cudaStream_t st) {
 #define SVK_G(K_, N_) if (KC == K_ && BN == N_) return launch_gather_t<K_, N_>(ta, tb, p, st)
   SVK_G(64, 32); SVK_G(64, 64); SVK_G(64, 128); SVK_G(64, 256);
@@ -399,6 +636,11 @@ int run_gather(const bf16* in, int N, int Hin, int Win, int Kc,           // gat
   p.prof = svk_prof_buffer();
   CUtensorMap ta, tb;
   if (int e = make_nhwc_map(&ta, in, N, Hin, Win, Kc, KC, p.bw, p.bh, es)) return e;
+  if (gather2_applicable(KC, BN, p)) {
+    p.pair = 1;
+    if (int e = make_w_map(&tb, w, (long long)ntaps_total * Nout, Kc, KC, BN / 2)) return e;     // each CTA loads half a filter block
+    return BN == 128 ? launch_gather2_t<64, 128>(ta, tb, p, st) : launch_gather2_t<64, 256>(ta, tb, p, st);
+  }
   if (int e = make_w_map(&tb, w, (long long)ntaps_total * Nout, Kc, KC, BN)) return e;
   return launch_gather(KC, BN, ta, tb, p, st);
 }

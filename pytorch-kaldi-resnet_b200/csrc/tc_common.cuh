@@ -28,6 +28,7 @@ struct GatherP {
   const bf16* bn_mask; const bf16* bn_c; const float* bn_mean; const float* bn_rstd;
   int dbg;                    // timing experiments only (SVK_DEBUG_SKIP=1: no filter loads, 2: no activation loads)
   unsigned long long* prof;   // SVK_PROF=1: per-role cycle counters (svk_debug_prof_read), else NULL
+  int pair;                   // 1: CTA-pair kernel (cta_group::2): accumulator-free barriers live in the pair's leader CTA
 };
 // prof[0] CTAs | MMA warp: [1] loop cycles [2] waiting for operands [3] waiting for a free accumulator |
 // producer: [4] loop cycles [5] waiting for a free stage | first epilogue warp: [6] loop cycles [7] waiting for an accumulator
@@ -53,6 +54,29 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// ---- CTA-pair (cluster of 2) helpers: address of the same smem offset in CTA `rank`, remote arrives
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (.release at CTA scope), like cutlass::arch::ClusterBarrier::arrive(cta_id): a .release.cluster arrive
+  // drains the SM's outstanding memory traffic first — ~1,000 cycles each inside a TMA-fed mainloop (measured)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  if (elect_one()) asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// accumulator-free signal of an epilogue warp: local barrier, or (CTA-pair kernels) the barrier of the pair's leader CTA
+__device__ __forceinline__ void tempty_arrive(uint32_t bar, int pair) {
+  if (pair) mbar_arrive_cluster(mapa_u32(bar, 0));
+  else mbar_arrive(bar);
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -84,6 +108,24 @@ __device__ __forceinline__ void prof_flush(unsigned long long* prof, int slot, l
   if (prof && lane == 0) {
     atomicAdd(prof + slot, (unsigned long long)total);
     atomicAdd(prof + slot + 1, (unsigned long long)waited);
+  }
+}
+// wait with cluster-scope acquire: the barrier is signalled from the other CTA of a pair
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  long long t0 = 0; bool timing = false;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (!timing) { t0 = clock64(); timing = true; }
+    else if (clock64() - t0 > 8000000000LL) {
+      printf("svk conv_tc: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      asm volatile("trap;");
+    }
   }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -302,7 +344,7 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) tempty_arrive(bar_tempty + 8 * acc, p.pair);
       if (ngroups == 2) aph ^= 1u;
       else if (++acc == 2) { acc = 0; aph ^= 1u; }
     }
@@ -473,7 +515,7 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) tempty_arrive(bar_tempty + 8 * acc, p.pair);
       if (!SPLIT && ngroups == 2) aph ^= 1u;
       else if (++acc == 2) { acc = 0; aph ^= 1u; }
       cur = nxt;

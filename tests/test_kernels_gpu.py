@@ -126,8 +126,9 @@ def test_conv_dgrad_bn_fusion(shape, impl, code):
                                  lib.BnBwdFuse(keep[0].data_ptr(), None, None, None, None), util.st())
 
 
-@pytest.mark.parametrize("env", [{"SVK_EPI2": "all"}, {"SVK_DISABLE_EPI2": "1"}, {"SVK_DISABLE_WGRAD9": "1", "SVK_DISABLE_WGRADR": "1"}],
-                         ids=["staged-epilogue-everywhere", "first-epilogue-only", "aligned-shift-wgrad"])
+@pytest.mark.parametrize("env", [{"SVK_EPI2": "all"}, {"SVK_DISABLE_EPI2": "1"}, {"SVK_DISABLE_WGRAD9": "1", "SVK_DISABLE_WGRADR": "1"},
+                                 {"SVK_ENABLE_PAIR": "1"}],
+                         ids=["staged-epilogue-everywhere", "first-epilogue-only", "aligned-shift-wgrad", "cta-pair-late-stages"])
 def test_conv_kernel_variants(env):
     """The library picks one kernel variant per shape (measured in the training step); the other variants stay selectable
     through the environment for A/B runs.  The switches are read once per process, so the convolution tests are re-run in a
