@@ -168,13 +168,13 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // HALF of the filter block (B, BN/2 rows); the leader CTA issues M = 256 x N = BN x K = 16 instructions that read both
 // CTAs' shared memory and write 128 accumulator rows into each CTA's TMEM.  The tensor pipe gains nothing from this
 // (tests/bench_umma.cu: cta_group::1 already runs N >= 128 tiles at the full rate) — the point is shared-memory INGEST: the
-// late stages wait for operands 44-46 % of their MMA loop at ~56 B/clk/SM (profiles/r01b_what_bounds_the_convs.md), and a
-// pair moves 25 % fewer bytes per MAC (A + B/2 instead of A + B per tile).  Epilogues are the single-CTA ones: every CTA
+// late stages stream single-use operands through shared memory (TMA write + UMMA read share 128 B/clk: 64 + N/2 cycles per
+// instruction, profiles/r01b_what_bounds_the_convs.md), and a pair moves 25 % fewer bytes per MAC (A + B/2 instead of A + B per
+// tile): 86 cycles per M=256 instruction measured at N = 128 against 143 per M=128 instruction of the single-CTA kernel.  Epilogues are the single-CTA ones: every CTA
 // drains its own accumulator rows and signals the leader's accumulator-free barrier (GatherP::pair).
-//   full[s]   (each CTA): its own producer's arrive.expect_tx + the bytes of its own TMA loads
-//   pfull[s]  (leader):   "the peer's stage s has landed" — relayed by the peer's (otherwise idle) MMA warp, ONE remote arrive
-//                         per stage (TMA loads that signal the leader's barrier directly, cp.async.bulk .cta_group::2, ran 1.85x
-//                         slower than the single-CTA kernel: every packet of the peer's loads sends a remote complete_tx)
+//   full[s]   (leader):   2 arrive.expect_tx (one per CTA's producer, default CTA-scope semantics: a .release.cluster arrive
+//                         costs ~1,000 cycles here) + the bytes of both CTAs' TMA loads (cp.async.bulk.tensor .cta_group::2
+//                         lets the peer's loads complete on the leader's barrier)
 //   empty[s]  (each CTA): multicast tcgen05.commit of the leader when the MMAs that read stage s have completed
 //   tfull[a]  (each CTA): multicast commit after the last MMA of a tile pair
 //   tempty[a] (leader):   one arrive per epilogue warp of BOTH CTAs
@@ -224,7 +224,7 @@ conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage0 = base;
   const uint32_t aux = base + Cfg::STAGES * Cfg::STAGE;
-  const uint32_t bar_full = aux, bar_empty = aux + 64, bar_tfull = aux + 128, bar_tempty = aux + 144, bar_pfull = aux + 192;
+  const uint32_t bar_full = aux, bar_empty = aux + 64, bar_tfull = aux + 128, bar_tempty = aux + 144;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + Cfg::STAGES * Cfg::STAGE + 160);
   float* scr = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE + SMEM_AUX);
   float* coef = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE + SMEM_AUX + SCR_BYTES);
@@ -235,7 +235,7 @@ conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   // arrivals that free an accumulator buffer: the epilogue warps of BOTH CTAs that drain it
   const uint32_t per_cta = (p.bn_mask && BN >= 128 && blockDim.x == GATHER_THREADS) ? 8u : 4u;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_pfull + 8 * s, 1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * per_cta); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -278,9 +278,10 @@ conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait_t(bar_empty + 8 * stage, ph ^ 1u, prof, pw);
           const uint32_t sa = stage0 + stage * Cfg::STAGE;
-          mbar_expect_tx(bar_full + 8 * stage, a_bytes + (uint32_t)Cfg::B_BYTES);
-          tma_load_4d(sa, &tmA, bar_full + 8 * stage, kc * KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full + 8 * stage, kc * KC, p.tap_w[t] * p.Nout + (int)rank * (BN / 2));
+          const uint32_t lfull = mapa_u32(bar_full + 8 * stage, 0);      // the leader's barrier of this stage
+          mbar_expect_tx_cluster(lfull, a_bytes + (uint32_t)Cfg::B_BYTES);
+          tma_load_4d_pair(sa, &tmA, lfull, kc * KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n);
+          tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, lfull, kc * KC, p.tap_w[t] * p.Nout + (int)rank * (BN / 2));
           if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; }
         }
       }
@@ -296,16 +297,13 @@ conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint64_t a_desc0 = make_desc(stage0, 16, Cfg::SBO, Cfg::LAYOUT);
       uint64_t a_desc = a_desc0;
       const bool prof = p.prof != nullptr;
-      long long pwf = 0, pwp = 0, pwt = 0; const long long pt0 = prof ? clock64() : 0;
+      long long pwf = 0, pwt = 0; const long long pt0 = prof ? clock64() : 0;
       for (int k = pair0; k < n_pairs; k += pair_step) {
         mbar_wait_t(bar_tempty + 8 * acc, aph ^ 1u, prof, pwt);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait_t(bar_full + 8 * stage, ph, prof, pwf);
-          { const long long t0 = prof ? clock64() : 0;
-            mbar_wait(bar_pfull + 8 * stage, ph);              // the peer's half of this stage has landed too
-            if (prof) pwp += clock64() - t0; }
           tc_fence_after();
           const uint64_t b_desc = a_desc + (uint64_t)(Cfg::A_BYTES >> 4);
           tc_mma_pair(d_tmem, a_desc, b_desc, idesc, ks != 0 ? 1u : 0u);
@@ -321,22 +319,7 @@ conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (prof && lane == 0) {
         atomicAdd(p.prof + 0, 1ull); atomicAdd(p.prof + 1, (unsigned long long)(clock64() - pt0));
         atomicAdd(p.prof + 2, (unsigned long long)pwf); atomicAdd(p.prof + 3, (unsigned long long)pwt);
-        atomicAdd(p.prof + 13, (unsigned long long)pwp);
       }
-    } else {
-      // peer CTA: relay "stage landed" to the leader, one remote arrive per stage
-      int stage = 0; uint32_t ph = 0;
-      const bool prof = p.prof != nullptr;
-      long long pwr = 0;
-      for (int k = pair0; k < n_pairs; k += pair_step) {
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait_t(bar_full + 8 * stage, ph, prof, pwr);
-          if (elect_one()) mbar_arrive_cluster(mapa_u32(bar_pfull + 8 * stage, 0));
-          __syncwarp();
-          if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; }
-        }
-      }
-      if (prof && lane == 0) atomicAdd(p.prof + 15, (unsigned long long)pwr);                  // peer relay: waiting for its own loads
     }
   } else {
     // the single-CTA epilogues: tile = blockIdx.x + j * gridDim.x = 2 * pair + rank
@@ -570,7 +553,7 @@ int launch_gather2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP
     configured = true;
   }
   const int n_pairs = (p.total_tiles + 1) / 2;
-  const int threads = p.bn_mask ? GATHER_THREADS : TC_THREADS;
+  const int threads = p.bn_mask ? GATHER_THREADS : TC_THREADS;     // 8 epilogue warps for the plain epilogue measured slower (10.38 vs 10.28 ms per step)
   // a pair needs two SMs of one TPC: ask the driver how many pairs can be resident at once (fewer than SMs / 2 when TPCs
   // have a single enabled SM) — a persistent grid larger than that runs in two waves
   static int max_pairs[2] = {0, 0};
@@ -592,14 +575,12 @@ int launch_gather2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP
   SVK_LAUNCH_CHECK("conv_tc_gather2");
   return 0;
 }
-// CTA-pair variant: one N block of 128 / 256 channels, 64-channel K chunks, at least one pair of tiles.  OFF by default:
-// measured equal to the single-CTA kernel (stage 3 fprop / dgrad 62.9 / 51.0 us vs 58.8 / 48.1; stage 4 47.7 / 35.9 vs
-// 46.4 / 36.3): it removes most of the operand waiting (32 k -> 23 k cycles per CTA) but a cta_group::2 instruction then
-// takes ~103 cycles instead of ~79 next to the TMA writes — the late stages are bound by shared-memory bandwidth (UMMA
-// operand reads + TMA writes of operands that are used once), not by the L2 -> SM path.  SVK_ENABLE_PAIR=1 selects it.
+// CTA-pair variant: one N block of 128 / 256 channels, 64-channel K chunks, at least one pair of tiles.  Stage 3 fprop / dgrad
+// 54.8 / 40.8 us against 58.8 / 48.1 for the single-CTA kernel, stage 4 45.0 / 35.1 against 46.4 / 36.3 (tests/bench_conv.py);
+// 10.34 -> 10.28 ms per training step.  SVK_DISABLE_PAIR=1 selects the single-CTA kernel.
 bool gather2_applicable(int KC, int BN, const GatherP& p) {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("SVK_ENABLE_PAIR"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (on < 0) { const char* e = getenv("SVK_DISABLE_PAIR"); on = (e && e[0] == '1') ? 0 : 1; }
   return on && KC == 64 && (BN == 128 || BN == 256) && p.n_blocks == 1 && p.total_tiles >= 2 && !p.dbg;
 }
 

@@ -77,8 +77,8 @@ def main():
             t_first = (~p[9]) & 0xFFFFFFFFFFFFFFFF
             start_spread = (p[11] - t_first) / 1e3
             end_spread = (p[10] - ((~p[12]) & 0xFFFFFFFFFFFFFFFF)) / 1e3
-            print("%-6s %-26s %8.4f | %9.1f %9.1f %9.1f | %9.1f %9.1f | %9.1f %9.1f   CTAs=%d  mma-loop span %.1f us (starts within %.1f, ends within %.1f), SM clock %.3f GHz, wait-peer %.1f, peer: producer waits slot %.1f, relay waits loads %.1f" % (
-                name, shape, e0.elapsed_time(e1), k[1], k[2], k[3], k[4], k[5], k[6], k[7], p[0], span_us, start_spread, end_spread, ghz, k[13], k[14], k[15]), flush=True)
+            print("%-6s %-26s %8.4f | %9.1f %9.1f %9.1f | %9.1f %9.1f | %9.1f %9.1f   CTAs=%d  mma-loop span %.1f us (starts within %.1f, ends within %.1f), SM clock %.3f GHz, peer producer waits slot %.1f" % (
+                name, shape, e0.elapsed_time(e1), k[1], k[2], k[3], k[4], k[5], k[6], k[7], p[0], span_us, start_spread, end_spread, ghz, k[14]), flush=True)
 
 
 if __name__ == "__main__":
