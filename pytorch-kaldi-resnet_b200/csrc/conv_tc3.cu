@@ -17,6 +17,9 @@ struct Gather3P {
   int a_stage_bytes;   // halo tile bytes rounded up to 1024
   int halo_bytes;      // bytes one halo TMA load delivers
   int n_stages;
+  int single;          // 1: ONE (bh+2) x (bw+2) halo tile per output tile; tap (r, s) is the A descriptor offset r' * pitch + s'
+                       //    (descriptors may start at any row: tests/umma_shift_test.cu), accumulator rows i * pitch + j with
+                       //    j >= bw discarded.  0: one (bh+2) x bw halo tile per filter column (bw % 8 == 0)
   // staged epilogue (epilogue_v2.cuh): operand tiles of the epilogue arrive by TMA, the output leaves by TMA
   int epi2;            // 0: first epilogue (tc_common.cuh)
   int aux_nbuf;        // aux buffers per epilogue group (2 when they fit)
@@ -95,6 +98,13 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int th = pt % p.tiles_h;
         const int n = pt / p.tiles_h;
         const int h0 = th * p.bh, w0 = tw * p.bw;
+        if (q.single) {
+          mbar_wait_t(bar_empty + 8 * stage, ph ^ 1u, prof, pw);
+          mbar_expect_tx(bar_full + 8 * stage, (uint32_t)q.halo_bytes);
+          tma_load_4d(stage0 + stage * q.a_stage_bytes, &tmA, bar_full + 8 * stage, 0, w0 - 1, h0 - 1, n);
+          if (++stage == q.n_stages) { stage = 0; ph ^= 1u; }
+          continue;
+        }
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
           mbar_wait_t(bar_empty + 8 * stage, ph ^ 1u, prof, pw);
@@ -130,6 +140,30 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         mbar_wait_t(bar_tempty + 8 * acc, aph ^ 1u, prof, pwt);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        if (q.single) {
+          // one halo tile: tap (r = t, s = l) reads rows shifted by r' * pitch + s' (fprop r' = t, s' = l; dgrad 2 - t, 2 - l)
+          mbar_wait_t(bar_full + 8 * stage, ph, prof, pwf);
+          tc_fence_after();
+          const uint64_t pix16 = (uint64_t)(ROWB >> 4);                               // one pixel row, in 16-byte units
+          const uint64_t prow16 = (uint64_t)(((uint32_t)p.pitch * ROWB) >> 4);        // one halo image row
+#pragma unroll
+          for (int l = 0; l < 3; ++l) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              const uint64_t ad_t = a_desc + (uint64_t)(DGRAD ? 2 - t : t) * prow16 + (uint64_t)(DGRAD ? 2 - l : l) * pix16;
+              const uint64_t bd_t = b_desc0 + (uint64_t)(((t * 3 + l) * B_BYTES) >> 4);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                tc_mma(d_tmem, ad_t + 2 * k, bd_t + 2 * k, idesc, (l | t | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(bar_empty + 8 * stage);
+          a_desc += a_stage16;
+          if (++stage == q.n_stages) { stage = 0; ph ^= 1u; a_desc = a_desc0; }
+          tc_commit(bar_tfull + 8 * acc);
+          if (++acc == 2) { acc = 0; aph ^= 1u; }
+          continue;
+        }
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
           mbar_wait_t(bar_full + 8 * stage, ph, prof, pwf);
@@ -221,6 +255,30 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
       if (cost < best - 1e-9) { best = cost; bbh = bh; bbw = bw; }
     }
   }
+  static int single_on = -1;
+  if (single_on < 0) { const char* e = getenv("SVK_DISABLE_SINGLE_HALO"); single_on = (e && e[0] == '1') ? 0 : 1; }
+  // measured inside the training step (per step, 13 launches each): 64 channels — fprop 0.626 -> 0.568 ms, fused dgrad
+  // 0.767 -> 0.719 ms; 32 channels — fprop unchanged, fused dgrad 0.908 -> 1.328 ms (its per-thread epilogue accesses do
+  // not like the narrower tiles), so the 32-channel stage keeps one halo tile per filter column.  SVK_SINGLE_HALO=all forces it.
+  static int single_all = -1;
+  if (single_all < 0) { const char* e = getenv("SVK_SINGLE_HALO"); single_all = (e && e[0] == 'a') ? 1 : 0; }
+  q.single = (single_on && (Nout == 64 || single_all)) ? 1 : 0;
+  p.pitch = 0;
+  if (q.single) {
+    // single-halo tiles: accumulator rows i * (bw + 2) + j; fewest tiles, then the smallest halo tile (bytes loaded per tile)
+    long long best_t = -1; int best_halo = 0;
+    for (int bw = 1; bw <= 126 && bw <= Wc; ++bw) {
+      const int P = bw + 2;
+      if ((bw + 2) > 256) break;
+      int bh = (128 - bw) / P + 1;                       // (bh - 1) * P + bw <= 128
+      if (bh > Hc) bh = Hc;
+      if (bh + 2 > 256) bh = 254;
+      const long long tiles = (long long)((Hc + bh - 1) / bh) * ((Wc + bw - 1) / bw);
+      const int halo = (bh + 2) * P;
+      if (best_t < 0 || tiles < best_t || (tiles == best_t && halo < best_halo)) { best_t = tiles; best_halo = halo; bbh = bh; bbw = bw; }
+    }
+    p.pitch = bbw + 2;
+  }
   p.bh = bbh; p.bw = bbw;
   p.tiles_h = (Hc + p.bh - 1) / p.bh;
   p.tiles_w = (Wc + p.bw - 1) / p.bw;
@@ -234,10 +292,11 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   p.prof = svk_prof_buffer();
   q.g = p;
   for (int l = 0; l < 3; ++l) q.col_dw[l] = dgrad ? 1 - l : l - 1;
-  q.halo_bytes = (p.bh + 2) * p.bw * ROWB;
-  // the three tap views read rows [shift*bw, shift*bw + 128): keep every stage large enough for the deepest view
-  int need_rows = 2 * p.bw + 128;
-  int rows = (p.bh + 2) * p.bw > need_rows ? (p.bh + 2) * p.bw : need_rows;
+  q.halo_bytes = (p.bh + 2) * (q.single ? p.pitch : p.bw) * ROWB;
+  // the tap views read rows [shift, shift + 128): keep every stage large enough for the deepest view
+  int need_rows = q.single ? 2 * p.pitch + 2 + 128 : 2 * p.bw + 128;
+  int rows = (p.bh + 2) * (q.single ? p.pitch : p.bw);
+  if (rows < need_rows) rows = need_rows;
   q.a_stage_bytes = (rows * ROWB + 1023) / 1024 * 1024;
   // staged epilogue: training forward (statistics, no scale / residual / ReLU) and the fused BatchNorm-backward dgrad
   static int epi2_on = -1;
@@ -279,7 +338,7 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
     q.aux_off = (int)((q.coef_off + COEF_BYTES + 1023) / 1024 * 1024);
   }
   CUtensorMap ta, tb, tx[4];
-  if (int e = make_nhwc_map(&ta, in, N, Hc, Wc, Kc, KC, p.bw, p.bh + 2, 1)) return e;
+  if (int e = make_nhwc_map(&ta, in, N, Hc, Wc, Kc, KC, q.single ? p.pitch : p.bw, p.bh + 2, 1)) return e;
   if (int e = make_w_map(&tb, w_packed, (long long)9 * Nout, Kc, KC, BN)) return e;
   for (int k = 0; k < 4; ++k) tx[k] = ta;            // placeholders for the unused maps
   if (q.epi2) {

@@ -68,12 +68,14 @@ __device__ __forceinline__ void gather_epilogue_v2(const GatherP& p, const CUten
   const bool has_aux = has_mask;                       // forward pass: no operand tiles, the slot is only a staging buffer
   const bool stats = p.stats != nullptr;
 
-  const int m = q * 32 + lane;                         // accumulator row = pixel index inside the tile
+  const int m = q * 32 + lane;                         // accumulator row m = i * pitch + j (pitch > bw: pad columns, discarded)
   const int rows_tile = p.bh * p.bw;
-  const bool in_tile = m < rows_tile;
-  const int i = m / p.bw, j = m - i * p.bw;
-  const uint32_t swz = (BN == 32) ? (uint32_t)((m >> 1) & 3) : (uint32_t)(m & 7);
-  const uint32_t row_off = (uint32_t)m * ROWB;
+  const int pitch = p.pitch ? p.pitch : p.bw;
+  const int i = m / pitch, j = m - i * pitch;
+  const bool in_tile = (i < p.bh) && (j < p.bw);
+  const int rb = i * p.bw + j;                         // its row in the staged [bh x bw] box tiles
+  const uint32_t swz = (BN == 32) ? (uint32_t)((rb >> 1) & 3) : (uint32_t)(rb & 7);
+  const uint32_t row_off = (uint32_t)rb * ROWB;
 
   // column pass: this thread sums channel pair cp over the rows rg, rg + RG, ...
   const int cp = tid_g % NP, rg = tid_g / NP;

@@ -28,6 +28,8 @@ struct GatherP {
   const bf16* bn_mask; const bf16* bn_c; const float* bn_mean; const float* bn_rstd;
   int dbg;                    // timing experiments only (SVK_DEBUG_SKIP=1: no filter loads, 2: no activation loads)
   unsigned long long* prof;   // SVK_PROF=1: per-role cycle counters (svk_debug_prof_read), else NULL
+  int pitch;                  // accumulator row m = i * pitch + j (0: pitch = bw).  pitch = bw + 2: rows with j >= bw are the
+                              // pad columns of a single-halo tile (conv_tc3.cu) and are discarded
   int pair;                   // 1: CTA-pair kernel (cta_group::2): accumulator-free barriers live in the pair's leader CTA
 };
 // prof[0] CTAs | MMA warp: [1] loop cycles [2] waiting for operands [3] waiting for a free accumulator |
@@ -233,7 +235,8 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
     const bool prof = p.prof != nullptr && warp == 2;
     long long pw = 0; const long long pt0 = prof ? clock64() : 0;
     const int m = q * 32 + lane;            // accumulator row = pixel index inside the tile (loop invariant)
-    const int i = m / p.bw, j = m - i * p.bw;
+    const int pitch = p.pitch ? p.pitch : p.bw;
+    const int i = m / pitch, j = m - i * pitch;
     for (int tile = blockIdx.x + group * gridDim.x; tile < p.total_tiles; tile += ngroups * gridDim.x) {
       const int nblk = tile % p.n_blocks;
       int pt = tile / p.n_blocks;
@@ -252,7 +255,7 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
         stat_blk = nblk;
       }
       const int hc = th * p.bh + i, wc = tw * p.bw + j;
-      bool valid = (i < p.bh) && (hc < p.Hc) && (wc < p.Wc);
+      bool valid = (i < p.bh) && (j < p.bw) && (hc < p.Hc) && (wc < p.Wc);
       const int oh = hc * p.o_mul + p.o_off_h, ow = wc * p.o_mul + p.o_off_w;
       const long long off = valid ? ((((long long)n * p.Hout + oh) * p.Wout + ow) * p.Nout + nblk * BN) : 0;
       bool zero_out = false;
@@ -389,7 +392,8 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
     const bool prof = p.prof != nullptr && warp == 2;
     long long pw = 0; const long long pt0 = prof ? clock64() : 0;
     const int m = q * 32 + lane;
-    const int i = m / p.bw, j = m - i * p.bw;
+    const int pitch = p.pitch ? p.pitch : p.bw;
+    const int i = m / pitch, j = m - i * pitch;
     const int tstep = SPLIT ? (int)gridDim.x : ngroups * (int)gridDim.x;
 
     auto tile_info = [&](int tile) {
@@ -400,7 +404,7 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
       const int th = pt % p.tiles_h;
       const int n = pt / p.tiles_h;
       const int hc = th * p.bh + i, wc = tw * p.bw + j;
-      t.valid = (i < p.bh) && (hc < p.Hc) && (wc < p.Wc);
+      t.valid = (i < p.bh) && (j < p.bw) && (hc < p.Hc) && (wc < p.Wc);
       const int oh = hc * p.o_mul + p.o_off_h, ow = wc * p.o_mul + p.o_off_w;
       t.off = t.valid ? ((((long long)n * p.Hout + oh) * p.Wout + ow) * p.Nout + t.nblk * BN) : 0;
       t.zero_out = false;

@@ -127,8 +127,8 @@ def test_conv_dgrad_bn_fusion(shape, impl, code):
 
 
 @pytest.mark.parametrize("env", [{"SVK_EPI2": "all"}, {"SVK_DISABLE_EPI2": "1"}, {"SVK_DISABLE_WGRAD9": "1", "SVK_DISABLE_WGRADR": "1"},
-                                 {"SVK_DISABLE_PAIR": "1"}],
-                         ids=["staged-epilogue-everywhere", "first-epilogue-only", "aligned-shift-wgrad", "single-cta-late-stages"])
+                                 {"SVK_DISABLE_PAIR": "1"}, {"SVK_DISABLE_SINGLE_HALO": "1"}, {"SVK_SINGLE_HALO": "all", "SVK_EPI2": "all"}],
+                         ids=["staged-epilogue-everywhere", "first-epilogue-only", "aligned-shift-wgrad", "single-cta-late-stages", "three-halo-loads", "single-halo-and-staged-epilogue-everywhere"])
 def test_conv_kernel_variants(env):
     """The library picks one kernel variant per shape (measured in the training step); the other variants stay selectable
     through the environment for A/B runs.  The switches are read once per process, so the convolution tests are re-run in a
