@@ -46,15 +46,15 @@ def ncu_traffic():
     """DRAM bytes per launch of the fprop/dgrad kernels from the committed ncu capture of this same command
     (profiles/summarize_ncu.py over `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`): a static figure measured
     under the profiler, reported beside the live timings; null when the capture is absent."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_conv_traffic.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01b_ncu_conv_traffic.json")
     try:
         with open(path) as f:
             g = json.load(f)["groups"]
-        ks = [g[k] for k in ("conv_tc_gather_kernel", "conv_tc_gather3_kernel") if k in g]
+        ks = [g[k] for k in ("conv_tc_gather_kernel", "conv_tc_gather2_kernel", "conv_tc_gather3_kernel") if k in g]
         n = sum(k["launches"] for k in ks)
         by = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks)
         return {"traffic": by / n, "traffic_unit": "DRAM bytes per launch (ncu, %d launches of one step)" % n,
-                "traffic_source": "profiles/r01_ncu_conv_traffic.json"}
+                "traffic_source": "profiles/r01b_ncu_conv_traffic.json"}
     except (OSError, KeyError, ValueError, ZeroDivisionError):
         return {}
 
