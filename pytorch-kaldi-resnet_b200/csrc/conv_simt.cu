@@ -296,14 +296,27 @@ __global__ void __launch_bounds__(256) wgrad_reduce_klane_kernel(const float* __
   }
 }
 
-// One thread per output: the better shape when there are many outputs and few partials (late stages).
+// Four consecutive outputs per thread (one float4 per partial, 8 partials in flight): the shape for many outputs and few
+// partials (late stages: 0.6-2.4 M outputs, 12-48 partials = 28 MB that are still L2-resident).  Fixed summation order.
 __global__ void __launch_bounds__(256) wgrad_reduce_flat_kernel(const float* __restrict__ ws, int ksplit, long long stride,
                                                                 float* __restrict__ dw, int Cout, int Cin, int taps) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < stride; i += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < ksplit; ++k) s += ws[(long long)k * stride + i];
-    int ci = (int)(i % Cin); long long r = i / Cin; int co = (int)(r % Cout); int t = (int)(r / Cout);
-    dw[((long long)co * Cin + ci) * taps + t] = s;
+  const long long nv = stride >> 2;                   // Cin % 4 == 0 on this path
+  for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < nv; iv += (long long)gridDim.x * blockDim.x) {
+    const float4* src = reinterpret_cast<const float4*>(ws) + iv;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = 0;
+    for (; k + 8 <= ksplit; k += 8) {
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = src[(long long)(k + u) * nv];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
+    }
+    for (; k < ksplit; ++k) { const float4 t = src[(long long)k * nv]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+    const long long i = iv << 2;
+    const int ci = (int)(i % Cin); const long long r = i / Cin; const int co = (int)(r % Cout); const int t = (int)(r / Cout);
+    float* o = dw + ((long long)co * Cin + ci) * taps + t;
+    o[0] = s.x; o[taps] = s.y; o[2 * taps] = s.z; o[3 * taps] = s.w;
   }
 }
 
@@ -470,7 +483,8 @@ SVK_API int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* 
     long long b = (stride + 31) / 32; if (b > cap) b = cap;
     wgrad_reduce_klane_kernel<<<(int)b, 256, 0, st>>>((const float*)workspace, ksplit, stride, dw_oihw, d->Cout, d->Cin, d->R * d->R);
   } else {
-    long long b = (stride + 255) / 256; if (b > cap) b = cap;
+    SVK_REQUIRE(d->Cin % 4 == 0 && stride % 4 == 0, SVK_E_UNSUPPORTED, "conv2d_wgrad: Cin=%d must be a multiple of 4", d->Cin);
+    long long b = (stride / 4 + 255) / 256; if (b > cap) b = cap;
     wgrad_reduce_flat_kernel<<<(int)b, 256, 0, st>>>((const float*)workspace, ksplit, stride, dw_oihw, d->Cout, d->Cin, d->R * d->R);
   }
   SVK_LAUNCH_CHECK("conv2d_wgrad(reduce)");

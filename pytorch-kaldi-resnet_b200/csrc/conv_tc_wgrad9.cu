@@ -138,23 +138,18 @@ conv_tc_wgrad9_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
     mbar_wait_t(bar_done, 0, p.prof != nullptr, ew);
     tc_fence_after();
     const int q = warp & 3;
-    const int m = q * 32 + lane;                        // accumulator row = atom * CK + co
-    const int atom = m / CK, co = m % CK;
+    const int m0 = q * 32;                              // first accumulator row of this warp: row = atom * CK + co
+    const int atom = m0 / CK, co0 = m0 % CK;            // (uniform per warp: CK is a multiple of 32)
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float* wsl = p.ws + (long long)ks * p.ws_stride;
+    float* scr = reinterpret_cast<float*>(gbase) + q * 1024;      // the operand stages are idle now: 4 KB of scratch per warp
     for (int j = 0; j < MMAS; ++j) {
-      const int r = 2 - (j * 2 + atom);                 // filter row of this accumulator row (< 0: padding rows)
+      const int r = 2 - (j * 2 + atom);                 // filter row of these accumulator rows (< 0: padding rows)
       for (int b = 0; b < 3; ++b) {
         for (int c = 0; c < CK / 32; ++c) {
           uint32_t v[32];
           tc_ld32(taddr + (uint32_t)(j * ACC_COLS + b * CK + c * 32), v);
-          if (r >= 0) {
-            float4* dst = reinterpret_cast<float4*>(wsl + ((long long)(r * 3 + b) * p.C + co) * p.C + c * 32);
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
-                                   __uint_as_float(v[4 * e + 3]));
-          }
+          if (r >= 0) store_chunk_rows(scr, v, wsl + ((long long)(r * 3 + b) * p.C + co0) * p.C + c * 32, p.C, lane);
         }
       }
     }

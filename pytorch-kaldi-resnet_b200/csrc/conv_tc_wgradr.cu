@@ -141,19 +141,16 @@ conv_tc_wgradr_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
     mbar_wait_t(bar_done, 0, p.prof != nullptr, ew);
     tc_fence_after();
     const int q = warp & 3;
-    const int co = mb * 128 + q * 32 + lane;
+    const int co0 = mb * 128 + q * 32;                  // first Cout row of this warp
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float* wsl = p.ws + (long long)ks * p.ws_stride;
+    float* scr = reinterpret_cast<float*>(gbase) + q * 1024;      // the operand stages are idle now: 4 KB of scratch per warp
     for (int c = 0; c < 2; ++c) {
       for (int s = 0; s < 3; ++s) {
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
           tc_ld32(taddr + (uint32_t)(c * ACC_COLS + s * 64 + h * 32), v);
-          float4* dst = reinterpret_cast<float4*>(wsl + ((long long)(r * 3 + s) * p.Cout + co) * p.Cin + nb * 128 + c * 64 + h * 32);
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
-                                 __uint_as_float(v[4 * e + 3]));
+          store_chunk_rows(scr, v, wsl + ((long long)(r * 3 + s) * p.Cout + co0) * p.Cin + nb * 128 + c * 64 + h * 32, p.Cin, lane);
         }
       }
     }

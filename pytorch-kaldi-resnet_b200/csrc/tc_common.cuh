@@ -534,6 +534,24 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
     if (prof) prof_flush(p.prof, 6, clock64() - pt0, pw, lane);
   }
 
+// Store a warp's 32 x 32 fp32 accumulator chunk (lane = row, v = its 32 columns) to global rows `row_stride` floats apart as
+// full 128-byte lines: the rows go through a 4 KB XOR-swizzled smem scratch and come back 4 rows x 128 B per instruction
+// (4 L1 wavefronts instead of the 32 of a lane-per-row float4 store).  All lanes must call it.
+__device__ __forceinline__ void store_chunk_rows(float* scr, const uint32_t (&v)[32], float* dst_row0, long long row_stride, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(scr + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int jr = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3);
+    const uint4 x = *reinterpret_cast<const uint4*>(scr + row * 32 + ((jr ^ (row & 7)) << 2));
+    *reinterpret_cast<uint4*>(dst_row0 + (long long)row * row_stride + jr * 4) = x;
+  }
+  __syncwarp();
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
