@@ -171,7 +171,9 @@ int planr(const svk_conv_desc* d, WgradRP* pp, size_t* smem_out) {
   p.Cin = d->Cin; p.Cout = d->Cout; p.n_n_blk = d->Cin / 128;
   p.PW = d->W + 1;
   SVK_REQUIRE(p.PW <= 256, SVK_E_UNSUPPORTED, "conv2d_wgradr: W=%d too wide", d->W);
-  // bh: fewest K steps per image (least round-up padding) among the tiles that leave room for >= 3 stages, else >= 2
+  // bh: least MMA time per image — K steps (with their round-up padding) x 192 cycles + ~600 cycles of per-tile barrier /
+  // descriptor overhead (one-row tiles of a 5x25 image were issue-bound) — among the tiles that leave room for >= 3 stages,
+  // else >= 2
   long long best = -1; int best_ns = 0;
   for (int want = 3; want >= 2 && best < 0; --want) {
     for (int bh = 1; bh <= d->H && bh <= 256; ++bh) {
@@ -179,7 +181,7 @@ int planr(const svk_conv_desc* d, WgradRP* pp, size_t* smem_out) {
       const int chunk = ((rows + 24) * 128 + 1023) / 1024 * 1024;   // K round-up (<= 15 rows) + 2 rows of view shift
       const int ns = (WR_SMEM_MAX - 2048) / (4 * chunk);
       if (ns < want) break;
-      const long long cost = (long long)((d->H + bh - 1) / bh) * ((rows + 15) / 16);
+      const long long cost = (long long)((d->H + bh - 1) / bh) * (((rows + 15) / 16) * 192 + 600);
       if (best < 0 || cost < best) { best = cost; p.bh = bh; p.rows = rows; p.chunk_bytes = chunk; best_ns = ns; }
     }
   }
