@@ -86,6 +86,12 @@ class SpeakerNetEngine(object):
         self._saved = None
         self.grad_ready_cb = None       # called as cb(bucket_index) during backward (data-parallel hook)
         self.fuse_bn_bwd = os.environ.get("SVK_DISABLE_BN_FUSE", "0") != "1"   # A/B switch for the dgrad-epilogue fusion
+        # Weight gradients run on a side stream: they only feed the optimizer / the gradient all-reduce, so their (tensor-
+        # bound) kernels can share the SMs with the HBM-bound BatchNorm passes of the main chain instead of queueing
+        # between them.  SVK_WGRAD_STREAM=0 keeps everything on one stream.
+        self.wgrad_side = os.environ.get("SVK_WGRAD_STREAM", "1") != "0"
+        self._side_stream = None
+        self._side_pending = {}
         self.debug_masked = set()       # debug taps that hold the gradient already multiplied by the ReLU mask
         self.debug = None               # tests set this to a dict to capture per-layer gradients (clones)
         self._index_modules()
@@ -529,6 +535,8 @@ class SpeakerNetEngine(object):
             sums2 = self._bsums[b.bn2.idx]
             g2 = b.bn2.mod
             omask = 0 if masked else out.data_ptr()
+            self._wait_side("dc2")           # the previous block's side-stream weight gradients still read these buffers
+            self._wait_side("dcd")
             if cd is not None:
                 _, _, mud, rsd = self._coefs(b.bnd)
                 gd = b.bnd.mod
@@ -556,7 +564,7 @@ class SpeakerNetEngine(object):
                 self.debug[b.name + ".conv2"] = dc2.clone()
                 if dcd is not None:
                     self.debug[b.name + ".downsample.0"] = dcd.clone()
-            self._wgrad(d2, b.conv2, a1, dc2)
+            self._wgrad(d2, b.conv2, a1, dc2, "dc2")
             # bn1 (+ReLU mask from a1): mask and sums come out of conv2's data-gradient epilogue
             _, _, mu1, rs1 = self._coefs(b.bn1)
             sums1 = self._bsums[b.bn1.idx]
@@ -568,13 +576,14 @@ class SpeakerNetEngine(object):
                 call.svk_conv2d_dgrad(d2, dc2.data_ptr(), b.conv2.w_dgrad.data_ptr(), da1.data_ptr(), 0, 0, 0, st)
                 call.svk_bn_bwd_reduce(da1.data_ptr(), a1.data_ptr(), c1.data_ptr(), mu1.data_ptr(), rs1.data_ptr(), 0, 0, 0,
                                        sums1.data_ptr(), Mo, Co, self.dcode, st)
+            self._wait_side("dc1")
             call.svk_bn_bwd_apply(da1.data_ptr(), 0 if fuse else a1.data_ptr(), c1.data_ptr(), mu1.data_ptr(), rs1.data_ptr(),
                                   g1.weight.data_ptr(), dc1.data_ptr(), 0, 0, 0, 0, 0, sums1.data_ptr(),
                                   self._gview[id(g1.weight)].data_ptr(), self._gview[id(g1.bias)].data_ptr(), 0, 0,
                                   Mo, Co, self.dcode, st)
             if self.debug is not None:
                 self.debug[b.name + ".conv1"] = dc1.clone()
-            self._wgrad(d1, b.conv1, xin, dc1)
+            self._wgrad(d1, b.conv1, xin, dc1, "dc1")
             dx = gbuf[2][:xin.numel()].view(xin.shape)
             # which BatchNorm consumes dx: the stem's, or bn2 of the block below (whose sums can only be fused when that
             # block has no downsample BN sharing the gradient)
@@ -587,7 +596,7 @@ class SpeakerNetEngine(object):
             if fuse:
                 bnf = bn_fuse(xin, *below) if below is not None else bn_fuse(xin)
             if cd is not None:
-                self._wgrad(dd, b.convd, xin, dcd)
+                self._wgrad(dd, b.convd, xin, dcd, "dcd")
                 if fuse:
                     call.svk_downsample_dgrad_bn(d1, dc1.data_ptr(), b.conv1.w_dgrad.data_ptr(), dd, dcd.data_ptr(),
                                                  b.convd.w_dgrad.data_ptr(), dx.data_ptr(), bnf, st)
@@ -635,15 +644,48 @@ class SpeakerNetEngine(object):
             if p.grad is not g:
                 p.grad = g
 
-    def _wgrad(self, d, conv, x, dy):
+    def _wgrad(self, d, conv, x, dy, tag=None):
+        """Weight gradient of one convolution.  With the side stream, `tag` names the gradient buffer `dy` lives in: the main
+        stream calls _wait_side(tag) before it overwrites that buffer."""
         need = lib.load().svk_conv2d_wgrad_workspace_bytes(d)
         if need == 0:
             raise lib.SvkError("svk_conv2d_wgrad_workspace_bytes failed: " + lib.load().svk_last_error_string().decode())
+        old = getattr(self, "_arena_bufs", {}).get("wgrad_ws")
+        if old is not None and old.numel() < (need + 3) // 4 and self._side_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._side_stream)     # the workspace is about to be replaced: let its readers finish
         ws = self._arena("wgrad_ws", ((need + 3) // 4,), torch.float32)
-        call.svk_conv2d_wgrad(d, x.data_ptr(), dy.data_ptr(), self._gview[id(conv.mod.weight)].data_ptr(), ws.data_ptr(),
-                              ws.numel() * 4, _stream())
+        if not self.wgrad_side or tag is None:
+            call.svk_conv2d_wgrad(d, x.data_ptr(), dy.data_ptr(), self._gview[id(conv.mod.weight)].data_ptr(), ws.data_ptr(),
+                                  ws.numel() * 4, _stream())
+            return
+        main = torch.cuda.current_stream()
+        if self._side_stream is None or self._side_stream.device != self.device:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        ready = torch.cuda.Event()
+        ready.record(main)                       # dy (written by the kernel just launched on the main stream) is complete
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            call.svk_conv2d_wgrad(d, x.data_ptr(), dy.data_ptr(), self._gview[id(conv.mod.weight)].data_ptr(), ws.data_ptr(),
+                                  ws.numel() * 4, _stream())
+            done = torch.cuda.Event()
+            done.record(side)
+        self._side_pending[tag] = done
+
+    def _wait_side(self, tag):
+        """The main stream is about to overwrite gradient buffer `tag`: wait for the side-stream kernel that reads it."""
+        ev = self._side_pending.pop(tag, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _join_side(self):
+        """Everything issued on the side stream so far becomes visible to the main stream (gradient buckets, optimizer)."""
+        if self._side_stream is not None and self._side_pending:
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            self._side_pending.clear()
 
     def _bucket_done(self, idx):
+        self._join_side()
         if self.grad_ready_cb is not None:
             self.grad_ready_cb(idx)
 
