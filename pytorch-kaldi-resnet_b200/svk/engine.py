@@ -638,7 +638,7 @@ class SpeakerNetEngine(object):
             self.debug["res.conv1"] = dc0.clone()
         call.svk_stem_conv_wgrad(sv["x"].data_ptr(), dc0.data_ptr(), self._gview[id(self.stem_conv.weight)].data_ptr(),
                                  B, F, T, C0, self.dcode, st)
-        self._bucket_done(2)
+        self._bucket_done(2, last=True)
         # publish gradients: p.grad is a view of the flat gradient buffer (overwrite semantics)
         for p, g in zip(self._params, self._grad_views):
             if p.grad is not g:
@@ -684,8 +684,16 @@ class SpeakerNetEngine(object):
             torch.cuda.current_stream().wait_stream(self._side_stream)
             self._side_pending.clear()
 
-    def _bucket_done(self, idx):
-        self._join_side()
+    def _bucket_done(self, idx, last=False):
+        """The gradients of bucket `idx` have been issued.  Mid-backward the main stream does NOT wait for the side stream:
+        the gradient all-reduce (svk/parallel.py) waits for `bucket_side_event` on its own stream instead; the last bucket
+        joins the streams (the optimizer follows)."""
+        self.bucket_side_event = None
+        if last:
+            self._join_side()
+        elif self._side_stream is not None and self._side_pending and self.grad_ready_cb is not None:
+            self.bucket_side_event = torch.cuda.Event()
+            self.bucket_side_event.record(self._side_stream)
         if self.grad_ready_cb is not None:
             self.grad_ready_cb(idx)
 

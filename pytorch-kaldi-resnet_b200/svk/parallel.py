@@ -28,7 +28,8 @@ class GradBucketer(object):
         self.use_avg = self.cuda and dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         self.pending = 0
 
-    def reduce_bucket(self, idx):
+    def reduce_bucket(self, idx, also_wait=None):
+        """`also_wait`: an event of another stream that wrote part of the bucket (the engine's weight-gradient stream)."""
         if self.world == 1:
             return
         lo, hi = self.ranges[idx]
@@ -40,6 +41,8 @@ class GradBucketer(object):
             ev.record(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
+                if also_wait is not None:
+                    self.comm_stream.wait_event(also_wait)
                 self._allreduce_mean(view)
             self.pending += 1
         else:
@@ -87,7 +90,7 @@ class DistributedDataParallel(nn.Module):
         eng.grad_ready_cb = self._on_bucket
 
     def _on_bucket(self, idx):
-        self.bucketer.reduce_bucket(idx)
+        self.bucketer.reduce_bucket(idx, getattr(self._eng, "bucket_side_event", None))
         if idx == self._last_bucket:
             self.bucketer.finish()
 
