@@ -92,6 +92,9 @@ class SpeakerNetEngine(object):
         self.wgrad_side = os.environ.get("SVK_WGRAD_STREAM", "1") != "0"
         self._side_stream = None
         self._side_pending = {}
+        # test hook: delay every side-stream weight gradient by this many GPU cycles, so that a missing stream dependency
+        # (the main stream overwriting a buffer the side stream still reads) produces wrong gradients deterministically
+        self._side_delay = int(os.environ.get("SVK_WGRAD_STREAM_DELAY_CYCLES", "0"))
         self.debug_masked = set()       # debug taps that hold the gradient already multiplied by the ReLU mask
         self.debug = None               # tests set this to a dict to capture per-layer gradients (clones)
         self._index_modules()
@@ -626,6 +629,7 @@ class SpeakerNetEngine(object):
         _, _, mu, rs = self._coefs(bn)
         sums = self._bsums[bn.idx]
         dc0 = gbuf[1][:c0.numel()].view(c0.shape)
+        self._wait_side("dc2")           # dc0 aliases the buffer the first block's conv2 weight gradient reads on the side stream
         amask = 0 if masked else a0.data_ptr()
         if not reduced:
             call.svk_bn_bwd_reduce(dO.data_ptr(), amask, c0.data_ptr(), mu.data_ptr(), rs.data_ptr(), 0, 0, 0,
@@ -666,6 +670,8 @@ class SpeakerNetEngine(object):
         ready.record(main)                       # dy (written by the kernel just launched on the main stream) is complete
         side.wait_event(ready)
         with torch.cuda.stream(side):
+            if self._side_delay:
+                torch.cuda._sleep(self._side_delay)
             call.svk_conv2d_wgrad(d, x.data_ptr(), dy.data_ptr(), self._gview[id(conv.mod.weight)].data_ptr(), ws.data_ptr(),
                                   ws.numel() * 4, _stream())
             done = torch.cuda.Event()

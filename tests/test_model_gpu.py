@@ -342,3 +342,48 @@ def test_loss_trajectory_follows_oracle(precision):
     tol = 0.02 if precision == "fp32" else 0.10
     assert all(abs(a - b) <= tol * max(1.0, abs(b)) for a, b in zip(got, ref)), (got, ref)
     assert got[-1] < got[0] - 0.5 and ref[-1] < ref[0] - 0.5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_weight_gradient_stream_is_equivalent_to_one_stream(precision):
+    """The engine runs weight gradients on a side stream (svk/engine.py::_wgrad).  On the same weights and batch the
+    gradients must agree with the single-stream run up to the rounding noise of the statistics atomics — checked on tiny,
+    ragged batches with the side stream artificially delayed, so that a missing stream dependency shows as garbage (regression:
+    the stem gradient buffer aliases the one the first block's conv2 weight gradient reads)."""
+    from model import NeuralSpeakerModel
+    from svk.loss import CrossEntropyLoss
+    g = torch.Generator().manual_seed(17)
+    batches = [(torch.randn(b, 40, t, generator=g), torch.randint(0, 7, (b,), generator=g))
+               for b, t in ((2, 24), (5, 40), (1, 64), (8, 24), (3, 33), (16, 24))]
+
+    def run(flag):
+        old = os.environ.get("SVK_WGRAD_STREAM")
+        os.environ["SVK_WGRAD_STREAM"] = flag
+        os.environ["SVK_WGRAD_STREAM_DELAY_CYCLES"] = "400000"      # ~0.2 ms per weight gradient: the side stream always lags
+        try:
+            torch.manual_seed(9)
+            with contextlib.redirect_stdout(io.StringIO()):
+                m = NeuralSpeakerModel(spk_num=7, feat_dim=40, pooling="mean+std", loss="AAM", precision=precision).cuda()
+        finally:
+            del os.environ["SVK_WGRAD_STREAM_DELAY_CYCLES"]
+            if old is None:
+                del os.environ["SVK_WGRAD_STREAM"]
+            else:
+                os.environ["SVK_WGRAD_STREAM"] = old
+        assert m.engine.wgrad_side == (flag == "1")
+        m.train()
+        crit = CrossEntropyLoss()
+        out = []
+        for rep in range(4):
+            for x, y in batches:
+                loss = crit(m(x.cuda(), y.cuda()), y.cuda())
+                loss.backward()
+                out.append((float(loss), m.engine.flat_grads.detach().double().cpu().clone()))
+        return out
+
+    side, one = run("1"), run("0")
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    for k, ((l1, g1), (l0, g0)) in enumerate(zip(side, one)):
+        assert np.isfinite(l1) and torch.isfinite(g1).all(), k
+        assert abs(l1 - l0) <= 1e-5 * max(1.0, abs(l0)), (k, l1, l0)
+        assert float((g1 - g0).abs().max()) <= tol * float(g0.abs().max()), (k, float((g1 - g0).abs().max()), float(g0.abs().max()))
