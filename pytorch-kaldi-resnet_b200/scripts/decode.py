@@ -121,19 +121,23 @@ def extract(model, dataset, indices, device, max_frames, on_result):
     pinned = [_pinned(k, "x", cap, torch.float32) for k in range(nslot)]
     pinned_len = [_pinned(k, "len", MAX_BATCH_UTTS, torch.int32) for k in range(nslot)]
 
+    pinned_np = [t.numpy() for t in pinned]                      # numpy views of the pinned slots: plain memcpy on the worker
+    pinned_len_np = [t.numpy() for t in pinned_len]              # threads (torch CPU ops would fan out over the OpenMP pool
+                                                                 # from every worker at once and make the timing erratic)
+
     def fill(slot, batch):                                       # host side only: no CUDA calls on the worker threads
         mats = [dataset[i][0] for i in batch]                    # (F, T_i) float32
         lens = [m.shape[1] for m in mats]
         tmax = max(lens)
-        host = pinned[slot][:len(mats) * feat_dim * tmax].view(len(mats), feat_dim, tmax)
+        n = len(mats) * feat_dim * tmax
+        host_np = pinned_np[slot][:n].reshape(len(mats), feat_dim, tmax)
         same = min(lens) == tmax
         if not same:
-            host.zero_()
+            host_np.fill(0.0)
         for r, m in enumerate(mats):
-            host[r, :, :m.shape[1]] = torch.from_numpy(np.ascontiguousarray(m))
-        hl = pinned_len[slot][:len(mats)]
-        hl.copy_(torch.tensor(lens, dtype=torch.int32))
-        return host, hl, same
+            host_np[r, :, :m.shape[1]] = m
+        pinned_len_np[slot][:len(mats)] = lens
+        return pinned[slot][:n].view(len(mats), feat_dim, tmax), pinned_len[slot][:len(mats)], same
 
     def collect(batch, emb):
         out = emb.float().cpu().numpy()                          # waits for that batch's kernels
