@@ -370,7 +370,9 @@ def extras(net, dev):
     ds = Mem()
     net.eval()
     out = {}
-    decode.extract(net, ds, list(range(32)), dev, 65536, lambda u, v: None)            # warm-up
+    # warm-up = one full pass: the engine's activation arenas and the pinned staging slots grow to their final sizes (their
+    # cudaMalloc / cudaHostAlloc calls took longer than the whole timed pass and made this number erratic)
+    decode.extract(net, ds, list(range(len(ds))), dev, 65536, lambda u, v: None)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     decode.extract(net, ds, list(range(len(ds))), dev, 65536, lambda u, v: out.__setitem__(u, v))
@@ -394,13 +396,13 @@ def extras(net, dev):
     # adaptive s-norm statistics (config 5 shape, bounded sample): 2,048 embeddings against a 50,000 x 256 cohort, top-300
     coh = torch.randn(50000, 256, device=dev)
     q = torch.randn(2048, 256, device=dev)
-    scoring.cohort_topk_meanstd(q[:64], coh, topk=300, device=dev)
+    scoring.cohort_topk_meanstd(q, coh, topk=300, block_rows=2048, device=dev)       # warm-up with the timed shapes (410 MB score block)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     scoring.cohort_topk_meanstd(q, coh, topk=300, block_rows=2048, device=dev)
     torch.cuda.synchronize()
     dt_sn = time.perf_counter() - t0
-    scoring.cohort_topk_meanstd(q[:64], coh, topk=300, device=dev, tf32=True)
+    scoring.cohort_topk_meanstd(q, coh, topk=300, block_rows=2048, device=dev, tf32=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     scoring.cohort_topk_meanstd(q, coh, topk=300, block_rows=2048, device=dev, tf32=True)
