@@ -251,6 +251,14 @@ int svk_segment_mean(const float* X, const int* order, const int* offsets, int n
 size_t svk_col_mean_workspace_bytes(long long n, int D);
 int svk_col_mean(const float* X, long long n, int D, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- diagnostics -------------------------- */
+/* With SVK_PROF=1 in the environment the tensor-core convolution kernels add per-role cycle counters to a 16-entry device
+ * table ([0] CTAs; MMA warp: [1] loop cycles, [2] waiting for operands, [3] waiting for a free accumulator; producer: [4]
+ * loop, [5] waiting for a free stage; first epilogue warp: [6] loop, [7] waiting for an accumulator; [8..12] globaltimer
+ * sums / extrema of the MMA loops; [14] the peer producer of a CTA pair).  Copies the table to `out16` (host) and clears
+ * it; SVK_E_UNSUPPORTED unless SVK_PROF=1.  No reference counterpart: tests/prof_conv.py, tests/prof_wgrad.py. */
+int svk_debug_prof_read(unsigned long long* out16);
+
 #ifdef __cplusplus
 }
 #endif
