@@ -90,6 +90,7 @@ class SpeakerNetEngine(object):
         # bound) kernels can share the SMs with the HBM-bound BatchNorm passes of the main chain instead of queueing
         # between them.  SVK_WGRAD_STREAM=0 keeps everything on one stream.
         self.wgrad_side = os.environ.get("SVK_WGRAD_STREAM", "1") != "0"
+        self.side_shortcut = os.environ.get("SVK_SIDE_SHORTCUT", "1") != "0"    # forward: 1x1/s2 shortcut convs on the side stream
         self._side_stream = None
         self._side_pending = {}
         # test hook: delay every side-stream weight gradient by this many GPU cycles, so that a missing stream dependency
@@ -354,15 +355,35 @@ class SpeakerNetEngine(object):
             a1 = self._buf(ws, "a1_%d" % bi, (B, Ho, Wo, Co))
             c2 = self._buf(ws, "c2_%d" % bi, (B, Ho, Wo, Co))
             out = self._buf(ws, "o_%d" % bi, (B, Ho, Wo, Co))
+            cd = dd = None
+            cd_done = None
+            if b.convd is not None:
+                # the 1x1/s2 shortcut convolution depends only on the block input: on the side stream it runs beside the
+                # BatchNorm passes of the main branch; the main stream waits for it before the block's last BatchNorm
+                dd = self._desc(B, H, W, b.convd)
+                cd = self._buf(ws, "cd_%d" % bi, (B, Ho, Wo, Co))
+                if self.wgrad_side and self.side_shortcut:
+                    main = torch.cuda.current_stream()
+                    if self._side_stream is None or self._side_stream.device != self.device:
+                        self._side_stream = torch.cuda.Stream(device=self.device)
+                    ready = torch.cuda.Event()
+                    ready.record(main)               # `cur` (and the zeroed statistics table) are complete
+                    self._side_stream.wait_event(ready)
+                    with torch.cuda.stream(self._side_stream):
+                        if self._side_delay:
+                            torch.cuda._sleep(self._side_delay)
+                        self._conv_fwd(dd, b.convd, cur, cd, stats=self._stats[b.bnd.idx])
+                        cd_done = torch.cuda.Event()
+                        cd_done.record(self._side_stream)
             self._conv_fwd(d1, b.conv1, cur, c1, stats=self._stats[b.bn1.idx])
             self._bn_train_act(b.bn1, c1, a1, Mo, 1)
             d2 = self._desc(B, Ho, Wo, b.conv2)
             self._conv_fwd(d2, b.conv2, a1, c2, stats=self._stats[b.bn2.idx])
-            cd = dd = None
             if b.convd is not None:
-                dd = self._desc(B, H, W, b.convd)
-                cd = self._buf(ws, "cd_%d" % bi, (B, Ho, Wo, Co))
-                self._conv_fwd(dd, b.convd, cur, cd, stats=self._stats[b.bnd.idx])
+                if cd_done is not None:
+                    torch.cuda.current_stream().wait_event(cd_done)
+                else:
+                    self._conv_fwd(dd, b.convd, cur, cd, stats=self._stats[b.bnd.idx])
                 self._bn_train_act(b.bn2, c2, out, Mo, 1, res=cd, bn_b=b.bnd)
             else:
                 self._bn_train_act(b.bn2, c2, out, Mo, 1, res=cur)
