@@ -249,3 +249,23 @@ def test_engine_gradient_buckets_cover_the_flat_buffer_in_reverse_layer_order():
     assert names[first_tail:] == ["fc1.weight", "fc1.bias", "last.weight"]
     assert all(n.startswith("res.layer4") for n in names[first_l4:first_tail])
     assert m.engine.bucket_of_block.count(1) == 3 and m.engine.bucket_of_block[-1] == 1
+
+
+def test_scored_trial_reader_matches_the_reference_parsing():
+    """scripts/compute_eer.py::read_scored_trials (shared with compute_min_dcf.py): scores in score-file order as float64,
+    labels from the trial list keyed by the id pair, and the reference's exception for a scored pair that is not a trial
+    (compute_eer.py:81-93).  Checked on the reference's own files from the back-end fixture."""
+    import tempfile
+    import compute_eer
+    fx = np.load(os.path.join(U.GOLDEN, "backend.npz"))
+    with tempfile.TemporaryDirectory() as d:
+        sp, tp = os.path.join(d, "scores"), os.path.join(d, "trials")
+        open(sp, "w").write(str(fx["file/scores"]))
+        open(tp, "w").write(str(fx["file/trials"]))
+        scores, labels = compute_eer.read_scored_trials(sp, tp)
+        assert scores.dtype == np.float64 and np.array_equal(scores, fx["scores"])
+        assert np.array_equal(labels, fx["labels"])
+        with open(sp, "a") as f:
+            f.write("uttX uttY 0.5\n")
+        with pytest.raises(Exception, match="Missing entry for uttX and uttY"):
+            compute_eer.read_scored_trials(sp, tp)
