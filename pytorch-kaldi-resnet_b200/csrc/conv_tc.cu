@@ -230,7 +230,6 @@ conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   float* coef = reinterpret_cast<float*>(gbase + Cfg::STAGES * Cfg::STAGE + SMEM_AUX + SCR_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the MMAs)
-  const int n_epi_warps = ((int)blockDim.x - 64) >> 5;     // 4 or 8; every one of them drains every tile it is scheduled on
 
   // arrivals that free an accumulator buffer: the epilogue warps of BOTH CTAs that drain it
   const uint32_t per_cta = (p.bn_mask && BN >= 128 && blockDim.x == GATHER_THREADS) ? 8u : 4u;
@@ -239,7 +238,6 @@ conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * per_cta); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  (void)n_epi_warps;
   if (p.scale) {
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
   }

@@ -39,8 +39,6 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// tile slots of an aux buffer (aux_slots of them are allocated): [0] mask / output, [1] c, [2] shortcut gradient
-
 // BN in {32, 64}.  Two epilogue groups (4 warps each); group g drains accumulator buffer g = every other tile of the CTA
 // and owns nbuf (1 or 2) aux buffers of aux_slots tile slots each: [0] mask / output, [1] c, [2] shortcut gradient.
 // aux = generic pointer to the aux region (1024-aligned), aux_s = its shared-space address.

@@ -112,24 +112,6 @@ __device__ __forceinline__ void prof_flush(unsigned long long* prof, int slot, l
     atomicAdd(prof + slot + 1, (unsigned long long)waited);
   }
 }
-// wait with cluster-scope acquire: the barrier is signalled from the other CTA of a pair
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  long long t0 = 0; bool timing = false;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) return;
-    if (!timing) { t0 = clock64(); timing = true; }
-    else if (clock64() - t0 > 8000000000LL) {
-      printf("svk conv_tc: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      asm volatile("trap;");
-    }
-  }
-}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   if (elect_one()) asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
