@@ -15,20 +15,20 @@ for _p in (_HERE, _PKG):
 import kaldi_io  # noqa: E402
 
 
-def compute_mean(ark_file):
-    rows = [np.asarray(vec, dtype=np.float64) for _key, vec in kaldi_io.read_vec_flt_ark(ark_file)]
-    mat = np.asarray(rows, dtype=np.float64).astype(np.float32)           # torch.FloatTensor(mat) (compute_mean.py:14)
-    print("speakers: {}, feat-dim: {}".format(mat.shape[0], mat.shape[1]))
+def embedding_table(ark_file):
+    """All vectors of the ark as one float32 matrix (text vectors parse to float64 first, like torch.FloatTensor(mat) at :14)."""
+    rows = [np.asarray(vec, dtype=np.float64) for _utt, vec in kaldi_io.read_vec_flt_ark(ark_file)]
+    return np.asarray(rows, dtype=np.float64).astype(np.float32)
+
+
+def main(argv=None):
+    ark_file, mean_file = (sys.argv[1:] if argv is None else argv)[:2]
+    table = embedding_table(ark_file)
+    print("speakers: {}, feat-dim: {}".format(*table.shape))
     from svk import scoring
-    return scoring.global_mean(mat).cpu().numpy()
-
-
-def main():
-    ark_file = sys.argv[1]
-    mean_file = sys.argv[2]
-    mean = compute_mean(ark_file)
-    with open(mean_file, 'w') as f:
-        f.write(' [ ' + ' '.join(map(str, mean)) + ' ]\n')
+    mean = scoring.global_mean(table).cpu().numpy()
+    with open(mean_file, 'w') as out:
+        out.write(" [ %s ]\n" % ' '.join(map(str, mean)))
     print("saved mean of {} in {}".format(ark_file, mean_file))
 
 

@@ -15,32 +15,42 @@ for _p in (_HERE, _PKG):
 import kaldi_io  # noqa: E402
 
 
-def compute_speaker_mean(ark_file, utt2spk_file):
-    utt2spk = {}
-    for line in open(utt2spk_file, 'r'):
-        utt, spk = line.strip().split()
-        utt2spk[utt] = spk
-    spk_index, seg, rows = {}, [], []
+def read_utt2spk(path):
+    """'utt spk' per line -> dict (two whitespace-separated fields, like the reference's unpacking at :11-13)."""
+    table = {}
+    with open(path) as f:
+        for line in f:
+            utt, spk = line.strip().split()
+            table[utt] = spk
+    return table
+
+
+def speaker_table(ark_file, utt2spk_file):
+    """-> (speakers in order of first appearance, float32 matrix of their mean embeddings)."""
+    speaker_of = read_utt2spk(utt2spk_file)
+    speakers, row_speaker, rows = [], [], []
+    slot = {}
     for utt, vec in kaldi_io.read_vec_flt_ark(ark_file):
-        if utt not in utt2spk:
-            raise Exception('{} not specified to any speaker'.format(utt))
-        seg.append(spk_index.setdefault(utt2spk[utt], len(spk_index)))
+        spk = speaker_of.get(utt)
+        if spk is None:
+            raise Exception('{} not specified to any speaker'.format(utt))      # same message as :19
+        if spk not in slot:
+            slot[spk] = len(speakers)
+            speakers.append(spk)
+        row_speaker.append(slot[spk])
         rows.append(np.asarray(vec, dtype=np.float64))
-    mat = np.asarray(rows, dtype=np.float64).astype(np.float32)
+    table = np.asarray(rows, dtype=np.float64).astype(np.float32)
     from svk import scoring
-    means = scoring.speaker_means(mat, np.asarray(seg), len(spk_index)).cpu().numpy()
-    print("speakers: {}, feat-dim: {}".format(len(spk_index), mat.shape[1]))
-    return {spk: means[i] for spk, i in spk_index.items()}                # dicts keep insertion order, like the reference's
+    means = scoring.speaker_means(table, np.asarray(row_speaker), len(speakers)).cpu().numpy()
+    print("speakers: {}, feat-dim: {}".format(len(speakers), table.shape[1]))
+    return speakers, means
 
 
-def main():
-    ark_file = sys.argv[1]
-    utt2spk_file = sys.argv[2]
-    mean_file = sys.argv[3]
-    speaker_mean = compute_speaker_mean(ark_file, utt2spk_file)
-    with open(mean_file, 'w') as f:
-        for spk in speaker_mean:
-            f.write(spk + ' [ ' + ' '.join(map(str, speaker_mean[spk])) + ' ]\n')
+def main(argv=None):
+    ark_file, utt2spk_file, mean_file = (sys.argv[1:] if argv is None else argv)[:3]
+    speakers, means = speaker_table(ark_file, utt2spk_file)
+    with open(mean_file, 'w') as out:
+        out.writelines("%s [ %s ]\n" % (spk, ' '.join(map(str, row))) for spk, row in zip(speakers, means))
     print("saved speaker mean in {}".format(mean_file))
 
 

@@ -34,44 +34,49 @@ from svk.loss import CrossEntropyLoss, target_rank  # noqa: E402
 from svk.optim import SGD  # noqa: E402
 from svk.parallel import DistributedDataParallel  # noqa: E402
 
-parser = argparse.ArgumentParser(description='B200-native ResNet speaker-embedding training')
-parser.add_argument('--train-list', type=str, help='training scp')
-parser.add_argument('--cv-list', type=str, help='cv scp')
-parser.add_argument('--utt2spkid', type=str, help='utt2spkid')
-parser.add_argument('--input-dim', type=int, required=True, help='input feature dimension')
-parser.add_argument('--spk-num', type=int, required=True, help='number of speakers')
-parser.add_argument('--pooling', type=str, default='mean', help='mean or mean+std')
-parser.add_argument('--loss-type', type=str, default='softmax', help='softmax, AAM or AAM-v1')
-parser.add_argument('--margin', type=float, default=0.2, help='margin for AAM')
-parser.add_argument('--scale', type=float, default=30, help='scale for AAM')
-parser.add_argument('--dataset', type=str, default='v1', help='v1 or v2')
-parser.add_argument('--min-chunk-size', default=200, type=int, help='minimum feature map length (ignored, as in the reference)')
-parser.add_argument('--max-chunk-size', default=400, type=int, help='chunk length in frames')
-parser.add_argument('--log-dir', type=str, required=True, help='logging directory')
-parser.add_argument('-a', '--arch', metavar='ARCH', default='resnet18', help='recorded in the checkpoint only')
-parser.add_argument('-j', '--workers', default=2, type=int, metavar='N', help='number of data loading workers')
-parser.add_argument('--epochs', default=10, type=int, metavar='N')
-parser.add_argument('--start-epoch', default=0, type=int, metavar='N')
-parser.add_argument('-b', '--batch-size', default=128, type=int, metavar='N',
-                    help='total batch size of all GPUs on the node')
-parser.add_argument('--lr', '--learning-rate', default=0.1, type=float, metavar='LR', dest='lr')
-parser.add_argument('--lr-final', '--final-learning-rate', default=0.0001, type=float, metavar='LR', dest='lr_final')
-parser.add_argument('--momentum', default=0.9, type=float, metavar='M')
-parser.add_argument('--wd', '--weight-decay', default=1e-4, type=float, metavar='W', dest='weight_decay')
-parser.add_argument('-p', '--print-freq', default=10, type=int, metavar='N')
-parser.add_argument('--resume', default='', type=str, metavar='PATH')
-parser.add_argument('-e', '--evaluate', dest='evaluate', action='store_true')
-parser.add_argument('--pretrained', dest='pretrained', type=str, help='use pre-trained model')
-parser.add_argument('--world-size', default=-1, type=int, help='number of nodes')
-parser.add_argument('--rank', default=-1, type=int, help='node rank')
-parser.add_argument('--dist-url', default='tcp://224.66.41.62:23456', type=str)
-parser.add_argument('--dist-backend', default='nccl', type=str)
-parser.add_argument('--seed', default=None, type=int)
-parser.add_argument('--gpu', default=None, type=int, help='GPU id to use.')
-parser.add_argument('--gpu-num', default=-1, type=int, help='GPU nums to use.')
-parser.add_argument('--multiprocessing-distributed', action='store_true')
-# beyond the reference: numerics mode of the kernels
-parser.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'], help='activation storage (fp32 = validation mode)')
+# The reference's command line (train_resnet.py:25-91), kept flag for flag: (flags, options) rows, fed to argparse below.
+_S, _I, _F = str, int, float
+_FLAGS = (
+    (("--train-list",), dict(type=_S, help="training scp")),
+    (("--cv-list",), dict(type=_S, help="cv scp")),
+    (("--utt2spkid",), dict(type=_S, help="utt2spkid")),
+    (("--input-dim",), dict(type=_I, required=True, help="input feature dimension")),
+    (("--spk-num",), dict(type=_I, required=True, help="number of speakers")),
+    (("--pooling",), dict(type=_S, default="mean", help="mean or mean+std")),
+    (("--loss-type",), dict(type=_S, default="softmax", help="softmax, AAM or AAM-v1")),
+    (("--margin",), dict(type=_F, default=0.2, help="margin for AAM")),
+    (("--scale",), dict(type=_F, default=30, help="scale for AAM")),
+    (("--dataset",), dict(type=_S, default="v1", help="v1 or v2")),
+    (("--min-chunk-size",), dict(type=_I, default=200, help="minimum feature map length (ignored, as in the reference)")),
+    (("--max-chunk-size",), dict(type=_I, default=400, help="chunk length in frames")),
+    (("--log-dir",), dict(type=_S, required=True, help="logging directory")),
+    (("-a", "--arch"), dict(metavar="ARCH", default="resnet18", help="recorded in the checkpoint only")),
+    (("-j", "--workers"), dict(type=_I, default=2, metavar="N", help="number of data loading workers")),
+    (("--epochs",), dict(type=_I, default=10, metavar="N")),
+    (("--start-epoch",), dict(type=_I, default=0, metavar="N")),
+    (("-b", "--batch-size"), dict(type=_I, default=128, metavar="N", help="total batch size of all GPUs on the node")),
+    (("--lr", "--learning-rate"), dict(type=_F, default=0.1, metavar="LR", dest="lr")),
+    (("--lr-final", "--final-learning-rate"), dict(type=_F, default=0.0001, metavar="LR", dest="lr_final")),
+    (("--momentum",), dict(type=_F, default=0.9, metavar="M")),
+    (("--wd", "--weight-decay"), dict(type=_F, default=1e-4, metavar="W", dest="weight_decay")),
+    (("-p", "--print-freq"), dict(type=_I, default=10, metavar="N")),
+    (("--resume",), dict(type=_S, default="", metavar="PATH")),
+    (("-e", "--evaluate"), dict(dest="evaluate", action="store_true")),
+    (("--pretrained",), dict(dest="pretrained", type=_S, help="use pre-trained model")),
+    (("--world-size",), dict(type=_I, default=-1, help="number of nodes")),
+    (("--rank",), dict(type=_I, default=-1, help="node rank")),
+    (("--dist-url",), dict(type=_S, default="tcp://224.66.41.62:23456")),
+    (("--dist-backend",), dict(type=_S, default="nccl")),
+    (("--seed",), dict(type=_I, default=None)),
+    (("--gpu",), dict(type=_I, default=None, help="GPU id to use.")),
+    (("--gpu-num",), dict(type=_I, default=-1, help="GPU nums to use.")),
+    (("--multiprocessing-distributed",), dict(action="store_true")),
+    # beyond the reference: numerics mode of the kernels
+    (("--precision",), dict(default="bf16", choices=["bf16", "fp32"], help="activation storage (fp32 = validation mode)")),
+)
+parser = argparse.ArgumentParser(description="B200-native ResNet speaker-embedding training")
+for _names, _opts in _FLAGS:
+    parser.add_argument(*_names, **_opts)
 
 best_acc1 = 0
 
