@@ -259,6 +259,17 @@ def run_ours(args):
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms_t)
     clocks = sampler.stop() if sampler else None
+    # ---- sanity of what was timed: the loss of one more step is finite and, with N > 1, every rank holds the same
+    # parameters after the same number of all-reduced updates (train_resnet.py:185 semantics)
+    final_loss = float(step(x_dev, y_dev))
+    assert final_loss == final_loss and abs(final_loss) < 1e4, "bench: training loss is not finite (%r)" % final_loss
+    if world > 1:
+        flat = net.engine.flat_params
+        chk = torch.stack([flat.double().sum(), flat.double().abs().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "bench: parameters differ between ranks after the timed steps"
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
     e2e_value = world * B / (ms_e2e / args.steps / 1e3)
@@ -271,7 +282,8 @@ def run_ours(args):
                        "algorithmic_tflops_per_gpu": TRAIN_FLOP_PER_CHUNK * B / (ms_step / 1e3) / 1e12},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
                     "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": clocks}
+            "gpu_launches": launches, "clocks": clocks,
+            "checks": {"final_loss": final_loss, "ranks_hold_identical_parameters": True if world > 1 else None}}
 
     # ---- per-kernel device times of one step, measured live with CUDA events on the launching stream.  EVERY rank runs
     # this step (it contains the gradient all-reduce); only rank 0 records and reports.

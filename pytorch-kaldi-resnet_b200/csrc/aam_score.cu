@@ -42,11 +42,24 @@ SVK_API int svk_l2norm_rows_bwd(const float* dxhat, const float* xhat, const flo
   return 0;
 }
 
+// A label outside [0, C) is a caller error (--spk-num mismatch, bad utt2spkid line).  torch's CrossEntropyLoss / scatter_
+// raise a device-side assert in that situation; so do we: message + trap, so the failure surfaces as a CUDA error on the
+// next synchronising call instead of an out-of-bounds read or a silently dropped target term.
+__device__ __forceinline__ void require_label(long long lbl, int C, int row, const char* what) {
+  if (lbl < 0 || lbl >= (long long)C) {
+    printf("svk %s: label %lld of row %d is outside [0, %d)\n", what, lbl, row, C);
+    __trap();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ AAM margin
 __global__ void __launch_bounds__(256) aam_margin_fwd_kernel(float* __restrict__ z, const long long* __restrict__ label,
                                                              float* __restrict__ cos_t, int B, int C, float cos_m,
                                                              float sin_m, float th, float mm, float s) {
   long long n = (long long)B * C;
+  if (blockIdx.x == 0) {
+    for (int b = threadIdx.x; b < B; b += blockDim.x) require_label(label[b], C, b, "aam_margin_fwd");
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i / C), c = (int)(i % C);
     float v = z[i];
@@ -115,6 +128,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ z
   __shared__ float sm[32];
   int b = blockIdx.x;
   const float* p = z + (long long)b * C;
+  require_label(label[b], C, b, "ce_fwd");
   float zt = p[label[b]];
   float mx = -INFINITY;
   for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, p[c]);

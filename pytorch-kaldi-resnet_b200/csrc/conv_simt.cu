@@ -330,12 +330,7 @@ int svk_downsample_dgrad_tc(const svk_conv_desc* d1, const void* dy1, const void
 int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats, int* ksplit_out,
                         cudaStream_t st);
 size_t svk_conv2d_wgrad_tc_ws_floats(const svk_conv_desc* d);
-// implemented in conv_tc_wgrad3.cu (3x3/s1, Cin == Cout in {32, 64}: taps stacked along M)
-bool svk_wgrad3_applicable(const svk_conv_desc* d);
-size_t svk_conv2d_wgrad3_tc_ws_floats(const svk_conv_desc* d);
-int svk_conv2d_wgrad3_tc(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats, int* ksplit_out,
-                         cudaStream_t st);
-// implemented in conv_tc_wgrad9.cu (same shapes: all nine taps in one UMMA through shifted operand views)
+// implemented in conv_tc_wgrad9.cu (3x3/s1, Cin == Cout in {32, 64}: all nine taps in one UMMA through shifted operand views)
 bool svk_wgrad9_applicable(const svk_conv_desc* d);
 size_t svk_conv2d_wgrad9_tc_ws_floats(const svk_conv_desc* d);
 int svk_conv2d_wgrad9_tc(const svk_conv_desc* d, const void* x, const void* dy, float* ws, size_t ws_floats, int* ksplit_out,
@@ -353,11 +348,6 @@ static bool wgradr_enabled() {
 static bool wgrad9_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SVK_DISABLE_WGRAD9"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v == 1;
-}
-static bool wgrad3_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SVK_DISABLE_WGRAD3"); v = (e && e[0] == '1') ? 0 : 1; }
   return v == 1;
 }
 
@@ -447,7 +437,6 @@ SVK_API size_t svk_conv2d_wgrad_workspace_bytes(const svk_conv_desc* d) {
   if (d->impl == SVK_IMPL_TCGEN05) {
     if (wgrad9_enabled() && svk_wgrad9_applicable(d)) return svk_conv2d_wgrad9_tc_ws_floats(d) * sizeof(float);
     if (wgradr_enabled() && svk_wgradr_applicable(d)) return svk_conv2d_wgradr_tc_ws_floats(d) * sizeof(float);
-    if (wgrad3_enabled() && svk_wgrad3_applicable(d)) return svk_conv2d_wgrad3_tc_ws_floats(d) * sizeof(float);
     return svk_conv2d_wgrad_tc_ws_floats(d) * sizeof(float);
   }
   long long ks; int gz;
@@ -468,8 +457,6 @@ SVK_API int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* 
       if (int e = svk_conv2d_wgrad9_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
     } else if (wgradr_enabled() && svk_wgradr_applicable(d)) {
       if (int e = svk_conv2d_wgradr_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
-    } else if (wgrad3_enabled() && svk_wgrad3_applicable(d)) {
-      if (int e = svk_conv2d_wgrad3_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
     } else {
       if (int e = svk_conv2d_wgrad_tc(d, x, dy, (float*)workspace, workspace_bytes / sizeof(float), &ksplit, st)) return e;
     }

@@ -95,10 +95,9 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait_t(bar_empty + 8 * stage, ph ^ 1u, prof, pw);
             const uint32_t sa = stage0 + stage * Cfg::STAGE;
-            mbar_expect_tx(bar_full + 8 * stage, ((p.dbg & 2) ? 0u : a_bytes) + ((p.dbg & 1) ? 0u : (uint32_t)Cfg::B_BYTES));
-            if (!(p.dbg & 2)) tma_load_4d(sa, &tmA, bar_full + 8 * stage, kc * KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n);
-            if (!(p.dbg & 1)) tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full + 8 * stage, kc * KC, p.tap_w[t] * p.Nout + nblk * BN);
-            if ((p.dbg & 3) == 3 && elect_one()) mbar_arrive(bar_full + 8 * stage);
+            mbar_expect_tx(bar_full + 8 * stage, a_bytes + (uint32_t)Cfg::B_BYTES);
+            tma_load_4d(sa, &tmA, bar_full + 8 * stage, kc * KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n);
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full + 8 * stage, kc * KC, p.tap_w[t] * p.Nout + nblk * BN);
             if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; }
           }
         }
@@ -579,7 +578,7 @@ int launch_gather2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP
 bool gather2_applicable(int KC, int BN, const GatherP& p) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("SVK_DISABLE_PAIR"); on = (e && e[0] == '1') ? 0 : 1; }
-  return on && KC == 64 && (BN == 128 || BN == 256) && p.n_blocks == 1 && p.total_tiles >= 2 && !p.dbg;
+  return on && KC == 64 && (BN == 128 || BN == 256) && p.n_blocks == 1 && p.total_tiles >= 2;
 }
 
 int launch_gather(int KC, int BN, const CUtensorMap& ta, const CUtensorMap& tb, const GatherP& p, cudaStream_t st) {
@@ -611,7 +610,6 @@ int run_gather(const bf16* in, int N, int Hin, int Win, int Kc,           // gat
   p.total_tiles = p.num_pix_tiles * p.n_blocks;
   p.kchunks = Kc / KC;
   p.Nout = Nout;
-  { const char* e = getenv("SVK_DEBUG_SKIP"); p.dbg = e ? atoi(e) : 0; }
   p.prof = svk_prof_buffer();
   CUtensorMap ta, tb;
   if (int e = make_nhwc_map(&ta, in, N, Hin, Win, Kc, KC, p.bw, p.bh, es)) return e;

@@ -259,10 +259,8 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   if (single_on < 0) { const char* e = getenv("SVK_DISABLE_SINGLE_HALO"); single_on = (e && e[0] == '1') ? 0 : 1; }
   // measured inside the training step (per step, 13 launches each): 64 channels — fprop 0.626 -> 0.568 ms, fused dgrad
   // 0.767 -> 0.719 ms; 32 channels — fprop unchanged, fused dgrad 0.908 -> 1.328 ms (its per-thread epilogue accesses do
-  // not like the narrower tiles), so the 32-channel stage keeps one halo tile per filter column.  SVK_SINGLE_HALO=all forces it.
-  static int single_all = -1;
-  if (single_all < 0) { const char* e = getenv("SVK_SINGLE_HALO"); single_all = (e && e[0] == 'a') ? 1 : 0; }
-  q.single = (single_on && (Nout == 64 || single_all)) ? 1 : 0;
+  // not like the narrower tiles), so the 32-channel stage keeps one halo tile per filter column.
+  q.single = (single_on && Nout == 64) ? 1 : 0;
   p.pitch = 0;
   if (q.single) {
     // single-halo tiles: accumulator rows i * (bw + 2) + j; fewest tiles, then the smallest halo tile (bytes loaded per tile)
@@ -301,15 +299,11 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   // staged epilogue: training forward (statistics, no scale / residual / ReLU) and the fused BatchNorm-backward dgrad
   static int epi2_on = -1;
   if (epi2_on < 0) { const char* e = getenv("SVK_DISABLE_EPI2"); epi2_on = (e && e[0] == '1') ? 0 : 1; }
-  const bool fwd_mode = !dgrad && p.stats && !p.scale && !p.res && !p.res_m && !p.relu && !p.valid_w && !p.bn_mask;
   const bool bwd_mode = dgrad && p.bn_mask && !p.res_m && !p.scale && !p.valid_w && !p.relu;
   // Measured inside the training step (profiles/r02_epilogue_v2.md): the staged epilogue wins where the first one is bound
   // by L1 wavefronts — the fused data gradient of the 64-channel stage (0.95 -> 0.74 ms per step) — and loses where a tile's
   // MMA time (32 channels: ~1,200 cycles) is shorter than its fixed barrier / store latencies, and in the forward pass.
-  // SVK_EPI2=all enables it everywhere it is implemented (A/B runs).
-  static int epi2_all = -1;
-  if (epi2_all < 0) { const char* e = getenv("SVK_EPI2"); epi2_all = (e && e[0] == 'a') ? 1 : 0; }
-  q.epi2 = (epi2_on && ((bwd_mode && Nout == 64) || (epi2_all && (fwd_mode || bwd_mode)))) ? 1 : 0;
+  q.epi2 = (epi2_on && bwd_mode && Nout == 64) ? 1 : 0;
   const size_t w_bytes = (size_t)9 * Kc * Nout * 2;
   size_t fixed = w_bytes + SMEM_AUX + SCR_BYTES + COEF_BYTES + 1024;
   size_t limit = 200 * 1024;

@@ -13,7 +13,7 @@
 //   * operand B = x tile loaded from column -1: MN-atom b starts b rows (pixels) further (LBO = ONE pixel): atoms
 //     b = 0,1,2 are the taps s = 0,1,2 stacked along N = 3C.
 //   D[(a, co), (b, ci)] += sum_k dyTile[k + a*PW][co] * xTile[k + b][ci]  is the whole 3x3 gradient: 1 (C=32) or 2 (C=64)
-//   UMMAs per 16 pixels instead of 3 / 6 (conv_tc_wgrad3.cu) or 9 (conv_tc.cu).  Where a shifted view wraps into the
+//   UMMAs per 16 pixels instead of 9 (conv_tc.cu).  Where a shifted view wraps into the
 //   next image row it meets a zero of the other operand (dy columns >= W, x column -1), so no masking is needed.
 // One CTA owns all 9 taps of a range of tiles (split-K over all SMs); partials go to the workspace with plain stores and
 // are reduced by wgrad_reduce_*_kernel (conv_simt.cu), like the other wgrad paths.

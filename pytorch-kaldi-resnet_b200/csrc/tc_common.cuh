@@ -26,7 +26,6 @@ struct GatherP {
   // dgrad only: BatchNorm-backward fusion (svk_bn_bwd_fuse).  out is zeroed where bn_mask <= 0; with bn_c the statistics
   // become  stats[ch] += sum(out), stats[Nout + ch] += sum(out * (bn_c - mean[ch]) * rstd[ch])  (mean/rstd staged in coef).
   const bf16* bn_mask; const bf16* bn_c; const float* bn_mean; const float* bn_rstd;
-  int dbg;                    // timing experiments only (SVK_DEBUG_SKIP=1: no filter loads, 2: no activation loads)
   unsigned long long* prof;   // SVK_PROF=1: per-role cycle counters (svk_debug_prof_read), else NULL
   int pitch;                  // accumulator row m = i * pitch + j (0: pitch = bw).  pitch = bw + 2: rows with j >= bw are the
                               // pad columns of a single-halo tile (conv_tc3.cu) and are discarded
@@ -555,11 +554,6 @@ inline int make_nhwc_map(CUtensorMap* m, const void* ptr, int N, int H, int W, i
   SVK_REQUIRE(enc, SVK_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  {   // timing experiment only (wrong results): SVK_DEBUG_NO_ESTRIDE=1 replaces strided boxes by dense ones
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("SVK_DEBUG_NO_ESTRIDE"); dbg = (e && e[0] == '1') ? 1 : 0; }
-    if (dbg) es = 1;
-  }
   cuuint32_t box[4] = {(cuuint32_t)ck, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   SVK_REQUIRE(box[1] <= 256 && box[2] <= 256, SVK_E_UNSUPPORTED, "conv_tc: TMA box %ux%u too large", box[1], box[2]);

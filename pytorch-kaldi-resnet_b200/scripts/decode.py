@@ -9,8 +9,9 @@ What changes underneath (the embeddings are the same, decode.py:198 `model.predi
     layer re-zeroes the padding, so each row equals its batch-1 result exactly (tests/test_model_gpu.py) while the
     launch count per utterance drops by the batch factor (batch 1 at ~40 launches per utterance is launch-bound);
   * BatchNorm is folded into the conv epilogues (eval mode); the host -> device copy of batch i+1 overlaps batch i.
-`-b/--batch-size` keeps its meaning of "total utterances in flight on the node" but values below 8 per GPU are raised
-to the frame budget below; `--chunk-size -1` (whole utterances) is what the recipes use.
+`-b/--batch-size` and `-j/--workers` are accepted for command-line compatibility and otherwise UNUSED: the batch is
+whatever fits the frame budget `--max-batch-frames`, and the reader is the mmap crop reader of kaldi_io (no worker
+processes).  `--chunk-size -1` (whole utterances) is what the recipes use.
 """
 import argparse
 import os
@@ -30,6 +31,7 @@ for _p in (_HERE, _PKG):
 
 from datasets import EmbeddingDataset  # noqa: E402
 from model import NeuralSpeakerModel  # noqa: E402
+from svk.ckpt import load_checkpoint  # noqa: E402
 from svk.parallel import shard_by_length  # noqa: E402
 
 parser = argparse.ArgumentParser(description='B200-native speaker-embedding extraction')
@@ -41,8 +43,8 @@ parser.add_argument('--chunk-size', default=-1, type=int, help='-1: whole uttera
 parser.add_argument('--model-path', type=str, required=True, help='checkpoint written by train_resnet.py')
 parser.add_argument('--world-size', default=-1, type=int)
 parser.add_argument('--rank', default=-1, type=int)
-parser.add_argument('-j', '--workers', default=2, type=int)
-parser.add_argument('-b', '--batch-size', default=8, type=int)
+parser.add_argument('-j', '--workers', default=2, type=int, help='accepted, unused (see module docstring)')
+parser.add_argument('-b', '--batch-size', default=8, type=int, help='accepted, unused: see --max-batch-frames')
 parser.add_argument('--dist-url', default='tcp://224.66.41.62:23456', type=str)
 parser.add_argument('--dist-backend', default='nccl', type=str)
 parser.add_argument('--seed', default=None, type=int)
@@ -190,7 +192,7 @@ def main_worker(gpu, ngpus_per_node, args):
         print("=> no checkpoint found at '{}'".format(args.model_path))
         return
     print("=> loading checkpoint '{}'".format(args.model_path))
-    checkpoint = torch.load(args.model_path, map_location='cpu', weights_only=False)
+    checkpoint = load_checkpoint(args.model_path, map_location='cpu')
     model.loadParameters(checkpoint['state_dict'])
     print("=> loaded checkpoint '{}' (epoch {})".format(args.model_path, checkpoint.get('epoch')))
     model.cuda(dev_index)

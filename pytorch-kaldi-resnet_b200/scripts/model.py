@@ -176,7 +176,8 @@ class NeuralSpeakerModel(nn.Module):
         with torch.no_grad():
             if self.training:
                 return self._engine.forward_train(x, None, with_head=False)
-            return self._engine.forward_eval(x, lengths=lengths)
+            from svk import ops
+            return ops.speaker_net_embed(self._engine, x, lengths)
 
     def loadParameters(self, loaded_state):
         """Shape-tolerant partial load that strips a leading 'module.' (model.py:415-432)."""

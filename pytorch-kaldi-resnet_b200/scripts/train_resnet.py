@@ -29,6 +29,7 @@ for _p in (_HERE, _PKG):
 
 from datasets import SequenceDataset, SequenceDataset2  # noqa: E402
 from model import NeuralSpeakerModel  # noqa: E402
+from svk.ckpt import load_checkpoint  # noqa: E402
 from svk.data import DevicePrefetcher  # noqa: E402
 from svk.loss import CrossEntropyLoss, target_rank  # noqa: E402
 from svk.optim import SGD  # noqa: E402
@@ -122,7 +123,7 @@ def main_worker(gpu, ngpus_per_node, args):
     if args.pretrained:
         if os.path.isfile(args.pretrained):
             print("=> using pre-trained model '{}'".format(args.pretrained))
-            checkpoint = torch.load(args.pretrained, map_location=loc, weights_only=False)
+            checkpoint = load_checkpoint(args.pretrained, map_location=loc)
             model.loadParameters(checkpoint['state_dict'])
         else:
             print("=> no pre-trained model found at '{}'".format(args.pretrained))
@@ -134,6 +135,17 @@ def main_worker(gpu, ngpus_per_node, args):
         model = DistributedDataParallel(model, device_ids=[args.gpu])
     print("gpu: {}, batch size: {}, args.workers:{}, ngpus_per_node: {}".format(gpu, args.batch_size, args.workers,
                                                                                ngpus_per_node))
+    # Without --gpu and without --multiprocessing-distributed the reference wraps the model in nn.DataParallel over all
+    # visible GPUs (train_resnet.py:190-199) and therefore checkpoints 'module.'-prefixed keys.  This drop-in trains that
+    # mode on ONE GPU (data parallelism here means one process per GPU: --multiprocessing-distributed), but keeps the key
+    # prefix so the checkpoint still --resume's in the reference.
+    key_prefix = ''
+    if not args.distributed and gpu is None:
+        key_prefix = 'module.'
+        if ngpus_per_node > 1:
+            warnings.warn('no --gpu / --multiprocessing-distributed: training on cuda:0 only (the reference would use '
+                          'nn.DataParallel over %d GPUs); pass --multiprocessing-distributed for one process per GPU'
+                          % ngpus_per_node)
     criterion = CrossEntropyLoss().cuda(args.gpu)
     optimizer = SGD(model.parameters(), args.lr, momentum=args.momentum, weight_decay=args.weight_decay)
     scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, args.epochs, eta_min=args.lr_final, last_epoch=-1)
@@ -141,7 +153,7 @@ def main_worker(gpu, ngpus_per_node, args):
     if args.resume:
         if os.path.isfile(args.resume):
             print("=> loading checkpoint '{}'".format(args.resume))
-            checkpoint = torch.load(args.resume, map_location=loc, weights_only=False)
+            checkpoint = load_checkpoint(args.resume, map_location=loc)
             args.start_epoch = checkpoint['epoch']
             best_acc1 = checkpoint['best_acc1']
             state = checkpoint['state_dict']
@@ -192,7 +204,7 @@ def main_worker(gpu, ngpus_per_node, args):
             save_checkpoint({
                 'epoch': epoch + 1,
                 'arch': args.arch,
-                'state_dict': {k: v.detach().clone() for k, v in model.state_dict().items()},
+                'state_dict': {key_prefix + k: v.detach().clone() for k, v in model.state_dict().items()},
                 'best_acc1': best_acc1,
                 'optimizer': optimizer.state_dict(),
             }, is_best, os.path.join(args.log_dir, 'checkpoint_epoch{}.pth.tar'.format(epoch)))

@@ -83,7 +83,8 @@ class SpeakerNetEngine(object):
         self._eval_ready = False
         self._packed_version = -1
         self._param_version = 0
-        self._saved = None
+        self._train_ws = {}             # (B, F, T) -> list of training workspaces; one per forward whose backward is pending
+        self._grads_fresh = False       # a backward wrote the flat gradient buffer and no optimizer step / zero_grad followed
         self.grad_ready_cb = None       # called as cb(bucket_index) during backward (data-parallel hook)
         self.fuse_bn_bwd = os.environ.get("SVK_DISABLE_BN_FUSE", "0") != "1"   # A/B switch for the dgrad-epilogue fusion
         # Weight gradients run on a side stream: they only feed the optimizer / the gradient all-reduce, so their (tensor-
@@ -201,6 +202,7 @@ class SpeakerNetEngine(object):
             self._stats = torch.zeros(nb, 2 * self._cmax, dtype=torch.float64, device=dev)
             self._bsums = torch.zeros(nb, 3 * self._cmax, dtype=torch.float64, device=dev)
         self._ws = {}
+        self._train_ws = {}
         self._eval_ready = False
         self._packed_version = -1
 
@@ -238,6 +240,25 @@ class SpeakerNetEngine(object):
                 self._ws.clear()
             ws = {}
             self._ws[key] = ws
+        return ws
+
+    def _lease_train_ws(self, key):
+        """A training workspace no pending backward still reads.  Saved-for-backward state (activations, BatchNorm
+        coefficients) lives in the workspace, so a second training-mode forward before backward() gets its OWN workspace
+        instead of overwriting the first one's (re-entrancy: two model(x, y) calls, or predict() in training mode)."""
+        pool = self._train_ws.setdefault(key, [])
+        for ws in pool:
+            if not ws["_busy"]:
+                return ws
+        if len(pool) >= 4:
+            raise lib.SvkError("%d training forwards of shape %s are waiting for their backward: call backward() (or run "
+                               "the extra forwards under torch.no_grad())" % (len(pool), (key,)))
+        if not pool and len(self._train_ws) > 4:      # a new batch shape: drop idle workspaces of other shapes
+            for k in [k for k, v in self._train_ws.items() if k != key and not any(w["_busy"] for w in v)]:
+                del self._train_ws[k]
+        ws = {"_busy": False,
+              "coef": torch.zeros(len(self.bns), 4, self._cmax, dtype=torch.float32, device=self.device)}
+        pool.append(ws)
         return ws
 
     def _buf(self, ws, name, shape, dtype=None):
@@ -321,8 +342,9 @@ class SpeakerNetEngine(object):
                            _ptr(bias), st)
 
     # ------------------------------------------------------------------------------------------ training forward
-    def forward_train(self, x, y, with_head=True):
-        """x: (B, F, T) fp32 CUDA, y: (B,) int64 -> logits (B, spk_num) fp32.  Saves activations for backward."""
+    def forward_train(self, x, y, with_head=True, save=True):
+        """x: (B, F, T) fp32 CUDA, y: (B,) int64 -> (logits (B, spk_num) fp32, saved state for backward_train).
+        with_head=False returns the embeddings only (predict() in training mode: batch statistics, nothing saved)."""
         self.ensure_device()
         self._param_version += 1        # parameters change every optimiser step: always re-pack, never reuse eval caches
         self._eval_ready = False
@@ -330,7 +352,8 @@ class SpeakerNetEngine(object):
         model = self.model
         B, F, T = x.shape
         x = x.contiguous().float()
-        ws = self._workspace(("train", B, F, T))
+        ws = self._lease_train_ws((B, F, T))
+        self._coef = ws["coef"]         # scale, shift, mean, rstd of every BatchNorm of THIS forward (read again by its backward)
         st = _stream()
         self._stats.zero_()
         self._nbt.add_(1)
@@ -403,8 +426,10 @@ class SpeakerNetEngine(object):
             return emb.clone()
         sv.update(last=cur, Hl=H, Wl=W, mode=mode, pooled=pooled, emb=emb, pdim=pdim, E=E)
         logits = self._head_fwd(emb, y, ws, sv, train=True)
-        self._saved = sv
-        return logits
+        if save:
+            ws["_busy"] = True          # released by backward_train, or when autograd drops the graph (_Lease.__del__)
+            sv["lease"] = _Lease(ws)
+        return logits, sv
 
     # ------------------------------------------------------------------------------------------ heads
     def _head_fwd(self, emb, y, ws, sv, train):
@@ -487,11 +512,18 @@ class SpeakerNetEngine(object):
         return dh
 
     # ------------------------------------------------------------------------------------------ training backward
-    def backward_train(self, dlogits):
-        sv = self._saved
-        if sv is None:
-            raise lib.SvkError("backward called without a saved forward")
-        self._saved = None
+    def backward_train(self, dlogits, sv):
+        """Backward of the forward that produced `sv`.  Parameter gradients are WRITTEN into the flat gradient buffer
+        (p.grad views); when the previous backward's gradients were not consumed by SGD.step() / zero_grad() they are
+        added on top, which is torch's accumulation semantics (the reference zeroes them every step, train_resnet.py:326)."""
+        if sv is None or sv.get("done"):
+            raise lib.SvkError("backward called twice for the same forward (retain_graph is not supported), or without one")
+        sv["done"] = True
+        keep = None
+        if self._grads_fresh:
+            self._join_side()
+            keep = self._grad.clone()
+        self._coef = sv["ws"]["coef"]
         model = self.model
         st = _stream()
         ws = sv["ws"]
@@ -668,6 +700,16 @@ class SpeakerNetEngine(object):
         for p, g in zip(self._params, self._grad_views):
             if p.grad is not g:
                 p.grad = g
+        if keep is not None:
+            self._grad.add_(keep)
+        self._grads_fresh = True
+        lease = sv.pop("lease", None)
+        if lease is not None:
+            lease.release()
+
+    def grads_consumed(self):
+        """SGD.step() / zero_grad(): the next backward overwrites the gradient buffer instead of accumulating into it."""
+        self._grads_fresh = False
 
     def _wgrad(self, d, conv, x, dy, tag=None):
         """Weight gradient of one convolution.  With the side stream, `tag` names the gradient buffer `dy` lives in: the main
@@ -812,22 +854,24 @@ def c_dtype_code(t):
     raise lib.SvkError("unsupported activation dtype %s" % t.dtype)
 
 
-class _NetFn(torch.autograd.Function):
-    """The whole network as ONE autograd node: forward = engine.forward_train, backward = engine.backward_train, which
-    writes parameter gradients straight into the flat gradient buffer (p.grad views) and returns no tensor grads."""
+class _Lease(object):
+    """Marks a training workspace busy until its backward has run — or until autograd frees the graph without one."""
+    __slots__ = ("ws",)
 
-    @staticmethod
-    def forward(ctx, engine, x, y, *params):
-        ctx.engine = engine
-        ctx.n = len(params)
-        return engine.forward_train(x, y)
+    def __init__(self, ws):
+        self.ws = ws
 
-    @staticmethod
-    def backward(ctx, dlogits):
-        ctx.engine.backward_train(dlogits)
-        return (None, None, None) + (None,) * ctx.n
+    def release(self):
+        if self.ws is not None:
+            self.ws["_busy"] = False
+            self.ws = None
+
+    def __del__(self):
+        self.release()
 
 
 def run_train(engine, x, y):
-    engine.ensure_device()
-    return _NetFn.apply(engine, x, y, *engine._params)
+    """Training forward as the registered custom op `svk::speaker_net_train` (svk/ops.py): autograd records ONE node whose
+    backward is `svk::speaker_net_train_backward`."""
+    from . import ops
+    return ops.speaker_net_train(engine, x, y)

@@ -6,7 +6,7 @@ otherwise one launch per parameter.  state_dict()/load_state_dict() use torch's 
 import torch
 from torch.optim import Optimizer
 
-from .lib import call
+from . import ops  # noqa: F401  (registers torch.ops.svk.*)
 
 
 class SGD(Optimizer):
@@ -56,16 +56,15 @@ class SGD(Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        st = torch.cuda.current_stream().cuda_stream
         if self._try_flatten():
             eng = self._engine
             g = self.param_groups[0]
             grads_ok = all(p.grad is gv for p, gv in zip(eng._params, eng._grad_views))
             if grads_ok:
-                call.svk_sgd_step(eng.flat_params.data_ptr(), eng.flat_grads.data_ptr(), self._flat_buf.data_ptr(),
-                                  eng.flat_params.numel(), float(g["lr"]), float(g["momentum"]),
-                                  float(g["weight_decay"]), float(self.grad_scale), st)
+                torch.ops.svk.sgd_step(eng.flat_params, eng.flat_grads, self._flat_buf, float(g["lr"]), float(g["momentum"]),
+                                       float(g["weight_decay"]), float(self.grad_scale))
                 eng.invalidate()
+                eng.grads_consumed()
                 return loss
         for g in self.param_groups:
             for p in g["params"]:
@@ -78,12 +77,17 @@ class SGD(Optimizer):
                     state["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 buf = state["momentum_buffer"]
                 grad = p.grad.contiguous()
-                call.svk_sgd_step(p.data_ptr(), grad.data_ptr(), buf.data_ptr(), p.numel(), float(g["lr"]),
-                                  float(g["momentum"]), float(g["weight_decay"]), float(self.grad_scale), st)
+                torch.ops.svk.sgd_step(p.data, grad, buf, float(g["lr"]), float(g["momentum"]), float(g["weight_decay"]),
+                                       float(self.grad_scale))
+        if self._engine is not None:
+            self._engine.invalidate()
+            self._engine.grads_consumed()
         return loss
 
     def zero_grad(self, set_to_none=True):
-        # Gradients are OVERWRITTEN by every backward of the engine, so nothing needs clearing on the flat path.
+        # The first backward after step() / zero_grad() OVERWRITES the flat gradient buffer (a second one before the next
+        # step() accumulates into it, like torch): nothing needs clearing on the flat path.
         if self._flat_buf is not None or self._try_flatten():
+            self._engine.grads_consumed()
             return
         super(SGD, self).zero_grad(set_to_none=set_to_none)

@@ -12,6 +12,7 @@ Embeddings are float32 on the device, exactly what the reference feeds torch (`t
 import torch
 
 from . import lib as _lib
+from . import ops  # noqa: F401  (registers torch.ops.svk.*)
 from .lib import call
 
 
@@ -32,13 +33,7 @@ def cosine_scores(enroll, test, mean, idx_enroll, idx_test, device="cuda"):
     E, T = _f32(enroll, device), _f32(test, device)
     ie, it = _i32(idx_enroll, device), _i32(idx_test, device)
     m = None if mean is None else _f32(mean, device)
-    n, D = ie.numel(), E.shape[1]
-    out = torch.empty(n, dtype=torch.float32, device=device)
-    if n == 0:
-        return out
-    call.svk_cosine_score_pairs(E.data_ptr(), T.data_ptr(), 0 if m is None else m.data_ptr(), ie.data_ptr(),
-                                it.data_ptr(), out.data_ptr(), n, D, _st())
-    return out
+    return torch.ops.svk.cosine_score_pairs(E, T, m, ie, it)
 
 
 def l2_normalize_rows(x, eps=1e-12):
@@ -78,7 +73,7 @@ def cohort_topk_meanstd(vecs, cohort, topk=300, block_rows=4096, device="cuda", 
                                0 if ws is None else ws.data_ptr(), need, st)
         else:
             call.svk_sgemm(xb.data_ptr(), D, 1, Cn.data_ptr(), 1, D, scores.data_ptr(), nc, rows, nc, D, 1.0, 0.0, 0, st)
-        call.svk_topk_meanstd(scores.data_ptr(), rows, nc, topk, mean[lo:].data_ptr(), std[lo:].data_ptr(), st)
+        mean[lo:lo + rows], std[lo:lo + rows] = torch.ops.svk.topk_meanstd(scores[:rows], topk)
     return mean, std
 
 
@@ -86,12 +81,7 @@ def snorm_apply(scores, idx_enroll, idx_test, mean_e, std_e, mean_t, std_t, devi
     s = _f32(scores, device)
     ie, it = _i32(idx_enroll, device), _i32(idx_test, device)
     me, se, mt, sd = _f32(mean_e, device), _f32(std_e, device), _f32(mean_t, device), _f32(std_t, device)
-    out = torch.empty_like(s)
-    if s.numel() == 0:
-        return out
-    call.svk_snorm_apply(s.data_ptr(), ie.data_ptr(), it.data_ptr(), me.data_ptr(), se.data_ptr(), mt.data_ptr(),
-                         sd.data_ptr(), out.data_ptr(), s.numel(), _st())
-    return out
+    return torch.ops.svk.snorm_apply(s, ie, it, me, se, mt, sd)
 
 
 def global_mean(vecs, device="cuda"):

@@ -49,7 +49,7 @@ def main(case, precision, B=2, T=48, impl=None):
     l2.backward()
     torch.cuda.synchronize()
     print("loss cuda %.7f oracle %.7f   logits rel err %.3e" % (float(l2), float(loss), util.rel_err(logits.detach().cpu(), out.detach())))
-    ws = eng._ws[("train", B, kw["feat_dim"], T)]
+    ws = eng._train_ws[(B, kw["feat_dim"], T)][0]
     outs = {b.name: ws["o_%d" % bi] for bi, b in enumerate(eng.blocks)}
     rows = []
     for nm, t in eng.debug.items():

@@ -56,6 +56,71 @@ def test_product_path_fails_loudly_without_cuda():
         m.predict(torch.zeros(1, 40, 16))
 
 
+def test_torch_custom_operators_are_registered_with_accurate_schemas():
+    """the C-ABI is wrapped as torch custom ops (torch.library.custom_op + register_autograd)."""
+    from svk import ops
+    for name in ops.REGISTERED:
+        assert hasattr(torch.ops.svk, name), name
+    s = str(torch.ops.svk.sgd_step.default._schema)
+    assert "Tensor(a0!) param" in s and "Tensor(a2!) momentum_buf" in s and "Tensor grad" in s
+    assert "Tensor(a1!) flat_grads" in str(torch.ops.svk.speaker_net_train_backward.default._schema)
+    assert "!" not in str(torch.ops.svk.cross_entropy.default._schema)
+    # CUDA-only kernels: a CPU tensor has no implementation to fall back to
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.svk.cross_entropy(torch.zeros(2, 3), torch.zeros(2, dtype=torch.long))
+    # fake (meta) kernels propagate shapes without touching the GPU
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        z = torch.empty(4, 10, device="cuda")
+        loss, lse = torch.ops.svk.cross_entropy(z, torch.empty(4, dtype=torch.long, device="cuda"))
+        assert loss.shape == () and lse.shape == (4,)
+        y = torch.ops.svk.conv2d(torch.empty(2, 10, 50, 128, dtype=torch.bfloat16, device="cuda"),
+                                 torch.empty(256, 128, 3, 3, device="cuda"), 2)
+        assert y.shape == (2, 5, 25, 256) and y.dtype == torch.bfloat16
+
+
+def test_network_operator_autograd_plumbing_without_a_gpu():
+    """The network-level op records ONE autograd node, hands the saved state of each forward to ITS backward (token), and
+    drops the state of a forward whose graph is freed or that ran under no_grad.  (CPU kernels registered for this test
+    only, around a stub engine: the real kernels are CUDA-only.)"""
+    import gc
+    from svk import ops
+
+    class StubEngine(object):
+        def __init__(self):
+            self._params = [torch.nn.Parameter(torch.randn(3)) for _ in range(4)]
+            self.flat_grads = torch.zeros(12)
+            self.calls = []
+
+        def ensure_device(self):
+            pass
+
+        def forward_train(self, x, y, with_head=True, save=True):
+            self.calls.append(("fwd", save))
+            return x.sum(2), {"id": len(self.calls)}
+
+        def backward_train(self, d, sv):
+            self.calls.append(("bwd", sv["id"]))
+    ops._speaker_net_train.register_kernel("cpu")(ops._speaker_net_train._init_fn)
+    ops._speaker_net_train_backward.register_kernel("cpu")(ops._speaker_net_train_backward._init_fn)
+    e = StubEngine()
+    x = torch.randn(2, 3, 4)
+    a = ops.speaker_net_train(e, x, None)
+    b = ops.speaker_net_train(e, x, None)
+    assert a.requires_grad and sorted(e._pending) == [1, 2]
+    b.sum().backward()
+    a.sum().backward()
+    assert e.calls == [("fwd", True), ("fwd", True), ("bwd", 2), ("bwd", 1)] and not e._pending
+    c = ops.speaker_net_train(e, x, None)
+    assert len(e._pending) == 1
+    del c
+    gc.collect()
+    assert not e._pending
+    with torch.no_grad():
+        d = ops.speaker_net_train(e, x, None)
+    assert not d.requires_grad and not e._pending and e.calls[-1] == ("fwd", False)
+
+
 # ------------------------------------------------------------------------------------------------ model interface
 def test_state_dict_keys_and_shapes_match_the_reference_layout():
     from model import NeuralSpeakerModel

@@ -126,9 +126,9 @@ def test_conv_dgrad_bn_fusion(shape, impl, code):
                                  lib.BnBwdFuse(keep[0].data_ptr(), None, None, None, None), util.st())
 
 
-@pytest.mark.parametrize("env", [{"SVK_EPI2": "all"}, {"SVK_DISABLE_EPI2": "1"}, {"SVK_DISABLE_WGRAD9": "1", "SVK_DISABLE_WGRADR": "1"},
-                                 {"SVK_DISABLE_PAIR": "1"}, {"SVK_DISABLE_SINGLE_HALO": "1"}, {"SVK_SINGLE_HALO": "all", "SVK_EPI2": "all"}],
-                         ids=["staged-epilogue-everywhere", "first-epilogue-only", "aligned-shift-wgrad", "single-cta-late-stages", "three-halo-loads", "single-halo-and-staged-epilogue-everywhere"])
+@pytest.mark.parametrize("env", [{"SVK_DISABLE_EPI2": "1"}, {"SVK_DISABLE_WGRAD9": "1", "SVK_DISABLE_WGRADR": "1"},
+                                 {"SVK_DISABLE_PAIR": "1"}, {"SVK_DISABLE_SINGLE_HALO": "1"}],
+                         ids=["first-epilogue-only", "generic-wgrad", "single-cta-late-stages", "three-halo-loads"])
 def test_conv_kernel_variants(env):
     """The library picks one kernel variant per shape (measured in the training step); the other variants stay selectable
     through the environment for A/B runs.  The switches are read once per process, so the convolution tests are re-run in a

@@ -110,7 +110,7 @@ def _train_once(m, fx, debug=True):
 def _engine_tensors(m, x):
     eng = m.engine
     B, Fd, T = x.shape
-    ws = eng._ws[("train", B, Fd, T)]
+    ws = eng._train_ws[(B, Fd, T)][0]
     names = {"res.conv1": ws["c0"]}
     for bi, b in enumerate(eng.blocks):
         names[b.name + ".conv1"] = ws["c1_%d" % bi]

@@ -1,0 +1,162 @@
+"""Multi-GPU parity on NCCL (SURVEY.md §4 "Distributed", Appendix C.4; needs >= 2 visible GPUs, skipped otherwise —
+run with `gpurun --gpus 2 -- python -m pytest tests/test_multigpu_gpu.py -m gpu`).
+
+The oracle of an N-rank step is NOT a single-GPU step on the concatenated batch (BatchNorm statistics are per rank,
+train_resnet.py:185 has no SyncBatchNorm): it is the reference forward/backward run independently on each rank's shard
+from identical weights, gradients averaged, one SGD step.  Checked here:
+  * the wrap-time broadcast makes every rank start from rank 0's parameters;
+  * step-1 gradients (after the bucketed all-reduce) are identical on all ranks and equal the MEAN of the per-rank
+    oracle gradients (fp32 validation mode <= 1e-4, bf16 product mode: cosine >= 0.99 per tensor);
+  * after K steps the parameters are BIT-identical across ranks, while the BatchNorm running statistics are local
+    (they differ between ranks and match each rank's own oracle statistics);
+  * decode.py and cosine_score.py under WORLD_SIZE = 2 produce the single-rank files.
+"""
+import contextlib
+import io
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import util
+from oracle import ref_model as O
+
+pytestmark = pytest.mark.gpu
+
+WORLD = 2
+
+
+def _need_gpus():
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
+
+
+def _torchrun(args, port, env=None):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(WORLD), "--master-addr",
+           "127.0.0.1", "--master-port", str(port)] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=util.ROOT, env=dict(os.environ, **(env or {})), timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_data_parallel_step_matches_per_rank_oracle(precision):
+    _need_gpus()
+    steps = 3
+    with tempfile.TemporaryDirectory() as tmp:
+        _torchrun([os.path.join(util.ROOT, "tests", "dist_worker.py"), tmp, precision, str(steps)], 29611 + (precision == "bf16"))
+        dumps = [torch.load(os.path.join(tmp, "rank%d.pt" % r), weights_only=False) for r in range(WORLD)]
+    d0 = dumps[0]
+    # (1) broadcast: every rank starts from rank 0's random init (ranks seeded differently)
+    for r in range(1, WORLD):
+        for k, v in d0["init"].items():
+            assert torch.equal(v, dumps[r]["init"][k]), "rank %d did not receive rank 0's %s" % (r, k)
+    # (2) step-1 gradients: identical across ranks, equal to the mean of the per-rank oracle gradients
+    for r in range(1, WORLD):
+        for k, v in d0["grads_step1"].items():
+            assert torch.equal(v, dumps[r]["grads_step1"][k]), "all-reduced gradient of %s differs on rank %d" % (k, r)
+    X, Y, per = d0["X"], d0["Y"], d0["per"]
+    names = O.param_names(d0["init"])
+    mean_grads = {n: torch.zeros_like(d0["init"][n]) for n in names}
+    rank_buffers = []
+    for r in range(WORLD):
+        sd = {k: v.clone() for k, v in d0["init"].items()}
+        for n in names:
+            sd[n].requires_grad_(True)
+        updates = {}
+        logits = O.model_forward(sd, X[0, r * per:(r + 1) * per], Y[0, r * per:(r + 1) * per], "mean+std", "AAM", 0.2, 30, True, updates)
+        O.cross_entropy(logits, Y[0, r * per:(r + 1) * per]).backward()
+        for n in names:
+            mean_grads[n] += sd[n].grad / WORLD
+        rank_buffers.append(updates)
+    worst, worst_cos = 0.0, 1.0
+    for n in names:
+        got, ref = d0["grads_step1"][n], mean_grads[n]
+        if precision == "fp32":
+            worst = max(worst, util.rel_err(got, ref))
+        elif ref.numel() >= 256:
+            worst_cos = min(worst_cos, float(F.cosine_similarity(got.reshape(1, -1), ref.reshape(1, -1))))
+    if precision == "fp32":
+        assert worst <= 1e-4, "gradient differs from the mean of the per-rank oracle gradients: %g" % worst
+    else:
+        assert worst_cos >= 0.98, "bf16 gradient cosine %g" % worst_cos
+    # (3) after K steps: parameters bit-identical across ranks, BatchNorm running statistics local
+    differs = 0
+    for k, v in d0["final"].items():
+        is_stat = k.endswith("running_mean") or k.endswith("running_var")
+        for r in range(1, WORLD):
+            if is_stat:
+                differs += int(not torch.equal(v, dumps[r]["final"][k]))
+            elif not k.endswith("num_batches_tracked"):
+                assert torch.equal(v, dumps[r]["final"][k]), "parameter %s diverged between ranks" % k
+    assert differs > 0, "BatchNorm running statistics are identical across ranks: they must stay local (no SyncBatchNorm)"
+    assert int(d0["final"]["res.bn1.num_batches_tracked"]) == steps
+
+
+def test_sharded_extraction_and_scoring_reproduce_single_rank_files():
+    """decode.py under --multiprocessing-distributed (one process per GPU, out_path/<gpu> files, the recipe's `cat`) and
+    cosine_score.py under torchrun give the files of a single-rank run (run_aam_v2.sh:115-135)."""
+    _need_gpus()
+    import kaldi_io
+    from model import NeuralSpeakerModel
+    rs = np.random.RandomState(5)
+    scripts = os.path.join(util.PKG, "scripts")
+    with tempfile.TemporaryDirectory() as tmp:
+        utts = ["utt%02d" % i for i in range(11)]
+        ark, scp = os.path.join(tmp, "feats.ark"), os.path.join(tmp, "feats.scp")
+        with open(ark, "wb") as f, open(scp, "w") as s:
+            for u in utts:
+                f.write((u + " ").encode())
+                off = f.tell()
+                kaldi_io.write_mat(f, rs.randn(int(rs.randint(40, 200)), 40).astype(np.float32))
+                s.write("%s %s:%d\n" % (u, ark, off))
+        torch.manual_seed(3)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = NeuralSpeakerModel(spk_num=9, feat_dim=40, pooling="mean+std", loss="AAM")
+        ck = os.path.join(tmp, "ck.pth.tar")
+        torch.save({"epoch": 1, "arch": "resnet34", "state_dict": m.state_dict(), "best_acc1": torch.zeros(1), "optimizer": {}}, ck)
+        common = ["--spk_num", "9", "--input-dim", "40", "--pooling", "mean+std", "--model-path", ck, "--decode-scp", scp]
+        one, two = os.path.join(tmp, "one"), os.path.join(tmp, "two")
+        r = subprocess.run([sys.executable, os.path.join(scripts, "decode.py")] + common + ["--out-path", one, "--gpu", "0"],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        r = subprocess.run([sys.executable, os.path.join(scripts, "decode.py")] + common +
+                           ["--out-path", two, "--multiprocessing-distributed", "--world-size", "1", "--rank", "0", "--gpu-num", "2",
+                            "--dist-url", "tcp://127.0.0.1:29631"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+        def read(paths):
+            out = {}
+            for p in paths:
+                for k, v in kaldi_io.read_vec_flt_ark(p):
+                    assert k not in out, "utterance %s extracted twice" % k
+                    out[k] = np.asarray(v)
+            return out
+        a = read([os.path.join(one, "0")])
+        b = read([os.path.join(two, "0"), os.path.join(two, "1")])
+        assert sorted(a) == sorted(b) == sorted(utts)
+        for u in utts:      # padded batches differ between the two runs, rows do not (batch-1 semantics)
+            assert np.abs(a[u] - b[u]).max() <= 1e-5 * max(1.0, np.abs(a[u]).max())
+        # scoring: trial blocks sharded over 2 ranks, merged in order
+        emb = os.path.join(tmp, "emb.iv")
+        with open(emb, "w") as f:
+            for u in utts:
+                f.write(u + " [ " + " ".join(map(str, a[u])) + " ]\n")
+        mean = os.path.join(tmp, "mean.vec")
+        with open(mean, "w") as f:
+            f.write(" [ " + " ".join(map(str, np.mean([a[u] for u in utts], 0))) + " ]\n")
+        trials = os.path.join(tmp, "trials")
+        with open(trials, "w") as f:
+            for i in range(57):
+                f.write("%s %s %s\n" % (utts[rs.randint(11)], utts[rs.randint(11)], "target" if i % 2 else "nontarget"))
+        args = ["--mean", mean, "--enroll", emb, "--test", emb, "--trials", trials]
+        r = subprocess.run([sys.executable, os.path.join(scripts, "cosine_score.py")] + args + ["--score-file", os.path.join(tmp, "s1")],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        _torchrun([os.path.join(scripts, "cosine_score.py")] + args + ["--score-file", os.path.join(tmp, "s2")], 29641)
+        assert open(os.path.join(tmp, "s1")).read() == open(os.path.join(tmp, "s2")).read()
