@@ -5,6 +5,7 @@
 // ------------------------------------------------------------------------------------------ row L2 normalise
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ xhat,
                                                          float* __restrict__ inv, int rows, int cols, float eps) {
+  pdl_prologue();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* p = x + (long long)warp * cols;
@@ -17,13 +18,14 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict
 }
 SVK_API int svk_l2norm_rows_fwd(const float* x, float* xhat, float* inv, int rows, int cols, float eps, void* stream) {
   SVK_REQUIRE(x && xhat && rows > 0 && cols > 0, SVK_E_BADARG, "l2norm_rows_fwd: bad args");
-  l2norm_fwd_kernel<<<(rows + 7) / 8, 256, 0, as_stream(stream)>>>(x, xhat, inv, rows, cols, eps);
+  svk_launch(l2norm_fwd_kernel, (rows + 7) / 8, 256, 0, as_stream(stream), x, xhat, inv, rows, cols, eps);
   SVK_LAUNCH_CHECK("l2norm_rows_fwd");
   return 0;
 }
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ dxhat, const float* __restrict__ xhat,
                                                          const float* __restrict__ inv, float* __restrict__ dx, int rows,
                                                          int cols) {
+  pdl_prologue();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* g = dxhat + (long long)warp * cols;
@@ -37,7 +39,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict
 SVK_API int svk_l2norm_rows_bwd(const float* dxhat, const float* xhat, const float* inv, float* dx, int rows, int cols,
                                 void* stream) {
   SVK_REQUIRE(dxhat && xhat && inv && dx && rows > 0 && cols > 0, SVK_E_BADARG, "l2norm_rows_bwd: bad args");
-  l2norm_bwd_kernel<<<(rows + 7) / 8, 256, 0, as_stream(stream)>>>(dxhat, xhat, inv, dx, rows, cols);
+  svk_launch(l2norm_bwd_kernel, (rows + 7) / 8, 256, 0, as_stream(stream), dxhat, xhat, inv, dx, rows, cols);
   SVK_LAUNCH_CHECK("l2norm_rows_bwd");
   return 0;
 }
@@ -56,6 +58,7 @@ __device__ __forceinline__ void require_label(long long lbl, int C, int row, con
 __global__ void __launch_bounds__(256) aam_margin_fwd_kernel(float* __restrict__ z, const long long* __restrict__ label,
                                                              float* __restrict__ cos_t, int B, int C, float cos_m,
                                                              float sin_m, float th, float mm, float s) {
+  pdl_prologue();
   long long n = (long long)B * C;
   if (blockIdx.x == 0) {
     for (int b = threadIdx.x; b < B; b += blockDim.x) require_label(label[b], C, b, "aam_margin_fwd");
@@ -76,13 +79,14 @@ SVK_API int svk_aam_margin_fwd(float* z, const long long* label, float* cos_t, i
                                float th, float mm, float s, void* stream) {
   SVK_REQUIRE(z && label && cos_t && B > 0 && C > 0, SVK_E_BADARG, "aam_margin_fwd: bad args");
   long long n = (long long)B * C; long long b = (n + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
-  aam_margin_fwd_kernel<<<(int)b, 256, 0, as_stream(stream)>>>(z, label, cos_t, B, C, cos_m, sin_m, th, mm, s);
+  svk_launch(aam_margin_fwd_kernel, (int)b, 256, 0, as_stream(stream), z, label, cos_t, B, C, cos_m, sin_m, th, mm, s);
   SVK_LAUNCH_CHECK("aam_margin_fwd");
   return 0;
 }
 __global__ void __launch_bounds__(256) aam_margin_bwd_kernel(float* __restrict__ g, const long long* __restrict__ label,
                                                              const float* __restrict__ cos_t, int B, int C, int ld,
                                                              float cos_m, float sin_m, float th, float s) {
+  pdl_prologue();
   long long n = (long long)B * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i / C), c = (int)(i % C);
@@ -103,7 +107,7 @@ SVK_API int svk_aam_margin_bwd(float* g, const long long* label, const float* co
                                float sin_m, float th, float s, void* stream) {
   SVK_REQUIRE(g && label && cos_t && B > 0 && C > 0 && ld >= C, SVK_E_BADARG, "aam_margin_bwd: bad args");
   long long n = (long long)B * C; long long b = (n + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
-  aam_margin_bwd_kernel<<<(int)b, 256, 0, as_stream(stream)>>>(g, label, cos_t, B, C, ld, cos_m, sin_m, th, s);
+  svk_launch(aam_margin_bwd_kernel, (int)b, 256, 0, as_stream(stream), g, label, cos_t, B, C, ld, cos_m, sin_m, th, s);
   SVK_LAUNCH_CHECK("aam_margin_bwd");
   return 0;
 }
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ z
                                                      float* __restrict__ loss_rows, float* __restrict__ lse,
                                                      int* __restrict__ rank, float* __restrict__ loss_mean, int B,
                                                      int C) {
+  pdl_prologue();
   __shared__ float sm[32];
   int b = blockIdx.x;
   const float* p = z + (long long)b * C;
@@ -148,13 +153,14 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ z
 SVK_API int svk_ce_fwd(const float* z, const long long* label, float* loss_rows, float* lse, int* rank,
                        float* loss_mean, int B, int C, void* stream) {
   SVK_REQUIRE(z && label && loss_rows && lse && B > 0 && C > 0, SVK_E_BADARG, "ce_fwd: bad args");
-  ce_fwd_kernel<<<B, 256, 0, as_stream(stream)>>>(z, label, loss_rows, lse, rank, loss_mean, B, C);
+  svk_launch(ce_fwd_kernel, B, 256, 0, as_stream(stream), z, label, loss_rows, lse, rank, loss_mean, B, C);
   SVK_LAUNCH_CHECK("ce_fwd");
   return 0;
 }
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ z, const long long* __restrict__ label,
                                                      const float* __restrict__ lse, const float* __restrict__ gout,
                                                      float mult, float* __restrict__ g, int B, int C) {
+  pdl_prologue();
   long long n = (long long)B * C;
   float gs = *gout * mult;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -167,7 +173,7 @@ SVK_API int svk_ce_bwd(const float* z, const long long* label, const float* lse,
                        float* g, int B, int C, void* stream) {
   SVK_REQUIRE(z && label && lse && gout && g && B > 0 && C > 0, SVK_E_BADARG, "ce_bwd: bad args");
   long long n = (long long)B * C; long long b = (n + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
-  ce_bwd_kernel<<<(int)b, 256, 0, as_stream(stream)>>>(z, label, lse, gout, mult, g, B, C);
+  svk_launch(ce_bwd_kernel, (int)b, 256, 0, as_stream(stream), z, label, lse, gout, mult, g, B, C);
   SVK_LAUNCH_CHECK("ce_bwd");
   return 0;
 }
@@ -178,6 +184,7 @@ __global__ void __launch_bounds__(256) cosine_pairs_kernel(const float* __restri
                                                            const float* __restrict__ mean, const int* __restrict__ ie,
                                                            const int* __restrict__ it, float* __restrict__ score,
                                                            long long ntrials, int D) {
+  pdl_prologue();
   long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -199,7 +206,7 @@ SVK_API int svk_cosine_score_pairs(const float* E, const float* T, const float* 
                                    float* score, long long ntrials, int D, void* stream) {
   SVK_REQUIRE(E && T && ie && it && score && ntrials > 0 && D > 0, SVK_E_BADARG, "cosine_score_pairs: bad args");
   long long b = (ntrials + 7) / 8; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
-  cosine_pairs_kernel<<<(int)b, 256, 0, as_stream(stream)>>>(E, T, mean, ie, it, score, ntrials, D);
+  svk_launch(cosine_pairs_kernel, (int)b, 256, 0, as_stream(stream), E, T, mean, ie, it, score, ntrials, D);
   SVK_LAUNCH_CHECK("cosine_score_pairs");
   return 0;
 }
@@ -217,6 +224,7 @@ __device__ inline float key2f(unsigned k) {
 }
 __global__ void __launch_bounds__(256) topk_meanstd_kernel(const float* __restrict__ scores, int ncoh, int topk,
                                                            float* __restrict__ mean, float* __restrict__ stdv) {
+  pdl_prologue();
   __shared__ int hist[2048];
   __shared__ int part[256];
   __shared__ unsigned s_prefix;
@@ -299,7 +307,7 @@ __global__ void __launch_bounds__(256) topk_meanstd_kernel(const float* __restri
 SVK_API int svk_topk_meanstd(const float* scores, int rows, int ncoh, int topk, float* mean, float* stdv, void* stream) {
   SVK_REQUIRE(scores && mean && stdv && rows > 0, SVK_E_BADARG, "topk_meanstd: bad args");
   SVK_REQUIRE(topk >= 2 && topk <= ncoh, SVK_E_BADARG, "topk_meanstd: need 2 <= topk (%d) <= ncoh (%d)", topk, ncoh);
-  topk_meanstd_kernel<<<rows, 256, 0, as_stream(stream)>>>(scores, ncoh, topk, mean, stdv);
+  svk_launch(topk_meanstd_kernel, rows, 256, 0, as_stream(stream), scores, ncoh, topk, mean, stdv);
   SVK_LAUNCH_CHECK("topk_meanstd");
   return 0;
 }
@@ -309,6 +317,7 @@ __global__ void __launch_bounds__(256) snorm_kernel(const float* __restrict__ sc
                                                     const int* __restrict__ it, const float* __restrict__ me,
                                                     const float* __restrict__ se, const float* __restrict__ mt,
                                                     const float* __restrict__ st, float* __restrict__ out, long long n) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float s = score[i];
     int e = ie[i], t = it[i];
@@ -319,7 +328,7 @@ SVK_API int svk_snorm_apply(const float* score, const int* ie, const int* it, co
                             const float* mt, const float* st, float* out, long long n, void* stream) {
   SVK_REQUIRE(score && ie && it && me && se && mt && st && out && n > 0, SVK_E_BADARG, "snorm_apply: bad args");
   long long b = (n + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
-  snorm_kernel<<<(int)b, 256, 0, as_stream(stream)>>>(score, ie, it, me, se, mt, st, out, n);
+  svk_launch(snorm_kernel, (int)b, 256, 0, as_stream(stream), score, ie, it, me, se, mt, st, out, n);
   SVK_LAUNCH_CHECK("snorm_apply");
   return 0;
 }

@@ -25,6 +25,7 @@ __device__ __forceinline__ unsigned long long key_image(double v) {
 
 __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const double* __restrict__ keys, long long n, int shift,
                                                                  int nblk, unsigned int* __restrict__ hist) {
+  pdl_prologue();
   __shared__ unsigned int h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const double* _
 
 // exclusive scan of `len` counters in place (one block; len = 256 * nblk is small: 131 k entries at 1 M keys)
 __global__ void __launch_bounds__(1024) scan_kernel(unsigned int* __restrict__ a, long long len) {
+  pdl_prologue();
   __shared__ unsigned long long part[1024];
   const long long per = (len + 1023) / 1024;
   const long long lo = (long long)threadIdx.x * per, hi = (lo + per < len) ? lo + per : len;
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const double
                                                                     double* __restrict__ keys_out, int* __restrict__ vals_out,
                                                                     long long n, int shift, int nblk,
                                                                     const unsigned int* __restrict__ offs) {
+  pdl_prologue();
   __shared__ unsigned int start[256];               // where this block's keys of each digit begin (+ those already placed)
   __shared__ unsigned int whist[SORT_THREADS / 32][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,6 +102,7 @@ constexpr int DET_CHUNK = DET_THREADS * DET_PER;
 
 __global__ void __launch_bounds__(DET_THREADS) det_blocksum_kernel(const int* __restrict__ lab, long long n,
                                                                    unsigned int* __restrict__ bsum) {
+  pdl_prologue();
   __shared__ unsigned int red[DET_THREADS];
   const long long base = (long long)blockIdx.x * DET_CHUNK + (long long)threadIdx.x * DET_PER;
   unsigned int s = 0;
@@ -121,6 +125,7 @@ __global__ void __launch_bounds__(DET_THREADS) det_eval_kernel(const int* __rest
                                                                const unsigned int* __restrict__ bsum, unsigned int n_t,
                                                                double p_target, double c_miss, double c_fa,
                                                                DetBest* __restrict__ out) {
+  pdl_prologue();
   __shared__ unsigned int tsum[DET_THREADS];
   __shared__ DetBest red[DET_THREADS];
   const long long base = (long long)blockIdx.x * DET_CHUNK + (long long)threadIdx.x * DET_PER;
@@ -163,6 +168,7 @@ __global__ void __launch_bounds__(DET_THREADS) det_eval_kernel(const int* __rest
 __global__ void __launch_bounds__(DET_THREADS) det_final_kernel(const DetBest* __restrict__ cand, int nblk, const int* __restrict__ lab,
                                                                 long long n, const unsigned int* __restrict__ bsum, unsigned int n_t,
                                                                 double* __restrict__ out) {
+  pdl_prologue();
   __shared__ DetBest red[DET_THREADS];
   DetBest b; b.v_eer = __longlong_as_double(0x7ff8000000000000ll); b.i_eer = n; b.v_dcf = __longlong_as_double(0x7ff0000000000000ll); b.i_dcf = n;
   for (int k = threadIdx.x; k < nblk; k += DET_THREADS) {
@@ -201,6 +207,7 @@ __global__ void __launch_bounds__(DET_THREADS) det_final_kernel(const DetBest* _
 // ---------------------------------------------------------------------------------------------- means
 __global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ X, const int* __restrict__ order,
                                                            const int* __restrict__ offsets, int D, float* __restrict__ out) {
+  pdl_prologue();
   const int seg = blockIdx.x;
   const int lo = offsets[seg], hi = offsets[seg + 1];
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -213,6 +220,7 @@ __global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restri
 // partial[b][d] = float64 sum of a slab of rows; a second launch (rows = number of slabs, scale = 1/n) finishes
 __global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ X, long long n, int D, long long rows_per,
                                                       double* __restrict__ partial) {
+  pdl_prologue();
   const long long lo = (long long)blockIdx.x * rows_per, hi = (lo + rows_per < n) ? lo + rows_per : n;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     double acc = 0.0;
@@ -222,6 +230,7 @@ __global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ 
 }
 __global__ void __launch_bounds__(256) col_mean_final_kernel(const double* __restrict__ partial, int nb, int D, long long n,
                                                              float* __restrict__ out) {
+  pdl_prologue();
   for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < D; d += gridDim.x * blockDim.x) {
     double acc = 0.0;
     for (int b = 0; b < nb; ++b) acc += partial[(size_t)b * D + d];
@@ -255,11 +264,11 @@ SVK_API int svk_sort_pairs_f64(const double* keys, const int* vals, double* keys
   for (int pass = 0; pass < 8; ++pass) {
     double* dk = (pass & 1) ? keys_out : tk;
     int* dv = (pass & 1) ? vals_out : tv;
-    sort_hist_kernel<<<nblk, SORT_THREADS, 0, st>>>(sk, n, pass * 8, nblk, hist);
+    svk_launch(sort_hist_kernel, nblk, SORT_THREADS, 0, st, sk, n, pass * 8, nblk, hist);
     SVK_LAUNCH_CHECK("sort_pairs_f64(hist)");
-    scan_kernel<<<1, 1024, 0, st>>>(hist, (long long)256 * nblk);
+    svk_launch(scan_kernel, 1, 1024, 0, st, hist, (long long)256 * nblk);
     SVK_LAUNCH_CHECK("sort_pairs_f64(scan)");
-    sort_scatter_kernel<<<nblk, SORT_THREADS, 0, st>>>(sk, sv, dk, dv, n, pass * 8, nblk, hist);
+    svk_launch(sort_scatter_kernel, nblk, SORT_THREADS, 0, st, sk, sv, dk, dv, n, pass * 8, nblk, hist);
     SVK_LAUNCH_CHECK("sort_pairs_f64(scatter)");
     sk = dk; sv = dv;
   }
@@ -282,13 +291,13 @@ SVK_API int svk_det_metrics(const int* sorted_labels, long long n, long long n_t
   uint8_t* w = (uint8_t*)workspace;
   unsigned int* bsum = (unsigned int*)w; w += align256((size_t)(nblk + 1) * 4);
   DetBest* cand = (DetBest*)w;
-  det_blocksum_kernel<<<nblk, DET_THREADS, 0, st>>>(sorted_labels, n, bsum);
+  svk_launch(det_blocksum_kernel, nblk, DET_THREADS, 0, st, sorted_labels, n, bsum);
   SVK_LAUNCH_CHECK("det_metrics(blocksum)");
-  scan_kernel<<<1, 1024, 0, st>>>(bsum, nblk);
+  svk_launch(scan_kernel, 1, 1024, 0, st, bsum, nblk);
   SVK_LAUNCH_CHECK("det_metrics(scan)");
-  det_eval_kernel<<<nblk, DET_THREADS, 0, st>>>(sorted_labels, n, bsum, (unsigned int)n_target, p_target, c_miss, c_fa, cand);
+  svk_launch(det_eval_kernel, nblk, DET_THREADS, 0, st, sorted_labels, n, bsum, (unsigned int)n_target, p_target, c_miss, c_fa, cand);
   SVK_LAUNCH_CHECK("det_metrics(eval)");
-  det_final_kernel<<<1, DET_THREADS, 0, st>>>(cand, nblk, sorted_labels, n, bsum, (unsigned int)n_target, out6);
+  svk_launch(det_final_kernel, 1, DET_THREADS, 0, st, cand, nblk, sorted_labels, n, bsum, (unsigned int)n_target, out6);
   SVK_LAUNCH_CHECK("det_metrics(final)");
   return 0;
 }
@@ -297,7 +306,7 @@ SVK_API int svk_segment_mean(const float* X, const int* order, const int* offset
   SVK_REQUIRE(n_seg >= 0 && D > 0, SVK_E_BADARG, "segment_mean: bad sizes");
   if (n_seg == 0) return 0;
   SVK_REQUIRE(X && order && offsets && out, SVK_E_BADARG, "segment_mean: null pointer");
-  segment_mean_kernel<<<n_seg, 256, 0, as_stream(stream)>>>(X, order, offsets, D, out);
+  svk_launch(segment_mean_kernel, n_seg, 256, 0, as_stream(stream), X, order, offsets, D, out);
   SVK_LAUNCH_CHECK("segment_mean");
   return 0;
 }
@@ -316,9 +325,9 @@ SVK_API int svk_col_mean(const float* X, long long n, int D, float* out, void* w
   const long long rows_per = (n + nb - 1) / nb;
   nb = (n + rows_per - 1) / rows_per;
   cudaStream_t st = as_stream(stream);
-  col_sum_kernel<<<(int)nb, 256, 0, st>>>(X, n, D, rows_per, (double*)workspace);
+  svk_launch(col_sum_kernel, (int)nb, 256, 0, st, X, n, D, rows_per, (double*)workspace);
   SVK_LAUNCH_CHECK("col_mean(sum)");
-  col_mean_final_kernel<<<(D + 255) / 256, 256, 0, st>>>((const double*)workspace, (int)nb, D, n, out);
+  svk_launch(col_mean_final_kernel, (D + 255) / 256, 256, 0, st, (const double*)workspace, (int)nb, D, n, out);
   SVK_LAUNCH_CHECK("col_mean(final)");
   return 0;
 }

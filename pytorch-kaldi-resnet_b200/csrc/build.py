@@ -16,8 +16,10 @@ def newest(paths):
     return max(os.path.getmtime(p) for p in paths)
 
 
-def build(force=False, verbose=False):
-    out = os.path.join(OUT_DIR, "libsvk.so")
+def build(force=False, verbose=False, extra_flags=(), out_name="libsvk.so"):
+    """extra_flags / out_name: A/B builds of kernel variants (`build.py --variant NAME -DX=1 ...` -> svk/libsvk_NAME.so,
+    selected at run time with SVK_LIB_PATH)."""
+    out = os.path.join(OUT_DIR, out_name)
     srcs = [os.path.join(HERE, s) for s in SOURCES]
     deps = srcs + [os.path.join(HERE, "svk_common.cuh"), os.path.join(HERE, "tc_common.cuh"),
                    os.path.join(HERE, "..", "..", "include", "svk.h")]
@@ -26,11 +28,12 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build", out_name.replace(".so", ""))
+    os.makedirs(bdir, exist_ok=True)
     for s in srcs:
-        o = os.path.join(HERE, "build", os.path.basename(s) + ".o")
+        o = os.path.join(bdir, os.path.basename(s) + ".o")
         objs.append(o)
-        procs.append((s, subprocess.Popen([nvcc] + FLAGS + ["-c", s, "-o", o], stdout=subprocess.PIPE,
+        procs.append((s, subprocess.Popen([nvcc] + FLAGS + list(extra_flags) + ["-c", s, "-o", o], stdout=subprocess.PIPE,
                                           stderr=subprocess.STDOUT, text=True)))
     log = []
     for s, p in procs:
@@ -39,7 +42,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write(text)
             raise RuntimeError("nvcc failed on %s" % s)
-    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
+    with open(os.path.join(bdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
@@ -50,4 +53,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build(force=True, extra_flags=[a for a in sys.argv[i + 2:] if a.startswith("-D")], out_name="libsvk_%s.so" % sys.argv[i + 1]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

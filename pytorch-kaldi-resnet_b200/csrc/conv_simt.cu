@@ -43,6 +43,7 @@ template <> __device__ inline void store4<__nv_bfloat16>(__nv_bfloat16* p, const
 // out[m, n] = sum_{tap, k} in[pix(m, tap), k] * w[tap][n][k]
 template <typename T, bool DGRAD>
 __global__ void __launch_bounds__(NT) conv_gather_kernel(GatherArgs a) {
+  pdl_prologue();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const T* in = (const T*)a.in;
@@ -144,6 +145,7 @@ struct WgradArgs {
 // partial[z][tap][co][ci] = sum over this z-slice's pixels of dy[pix, co] * x[shift_tap(pix), ci]
 template <typename T>
 __global__ void __launch_bounds__(NT) conv_wgrad_simt_kernel(WgradArgs a) {
+  pdl_prologue();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const T* x = (const T*)a.x;
@@ -227,8 +229,8 @@ int svk_conv2d_fwd_simt(const svk_conv_desc* d, const void* x, const void* w, vo
                nullptr, nullptr, relu, valid_wo};
   long long M = (long long)d->N * d->Ho * d->Wo;
   dim3 grid((unsigned)((M + BM - 1) / BM), (d->Cout + BN - 1) / BN);
-  if (d->dtype == SVK_F32) conv_gather_kernel<float, false><<<grid, NT, 0, st>>>(a);
-  else conv_gather_kernel<__nv_bfloat16, false><<<grid, NT, 0, st>>>(a);
+  if (d->dtype == SVK_F32) svk_launch(conv_gather_kernel<float, false>, grid, NT, 0, st, a);
+  else svk_launch(conv_gather_kernel<__nv_bfloat16, false>, grid, NT, 0, st, a);
   SVK_LAUNCH_CHECK("conv2d_fwd(simt)");
   return 0;
 }
@@ -238,8 +240,8 @@ int svk_conv2d_dgrad_simt(const svk_conv_desc* d, const void* dy, const void* w,
                res_m, mask, 0, nullptr};
   long long M = (long long)d->N * d->H * d->W;
   dim3 grid((unsigned)((M + BM - 1) / BM), (d->Cin + BN - 1) / BN);
-  if (d->dtype == SVK_F32) conv_gather_kernel<float, true><<<grid, NT, 0, st>>>(a);
-  else conv_gather_kernel<__nv_bfloat16, true><<<grid, NT, 0, st>>>(a);
+  if (d->dtype == SVK_F32) svk_launch(conv_gather_kernel<float, true>, grid, NT, 0, st, a);
+  else svk_launch(conv_gather_kernel<__nv_bfloat16, true>, grid, NT, 0, st, a);
   SVK_LAUNCH_CHECK("conv2d_dgrad(simt)");
   return 0;
 }
@@ -263,8 +265,8 @@ int svk_conv2d_wgrad_simt(const svk_conv_desc* d, const void* x, const void* dy,
   simt_wgrad_plan(d, &a.kslice, &gz);
   SVK_REQUIRE((size_t)gz * d->R * d->R * d->Cout * d->Cin <= ws_floats, SVK_E_BADARG, "conv2d_wgrad(simt): workspace too small");
   dim3 grid(gx, gy, gz);
-  if (d->dtype == SVK_F32) conv_wgrad_simt_kernel<float><<<grid, NT, 0, st>>>(a);
-  else conv_wgrad_simt_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(a);
+  if (d->dtype == SVK_F32) svk_launch(conv_wgrad_simt_kernel<float>, grid, NT, 0, st, a);
+  else svk_launch(conv_wgrad_simt_kernel<__nv_bfloat16>, grid, NT, 0, st, a);
   SVK_LAUNCH_CHECK("conv2d_wgrad(simt)");
   *ksplit_out = gz;
   return 0;
@@ -276,6 +278,7 @@ int svk_conv2d_wgrad_simt(const svk_conv_desc* d, const void* x, const void* dy,
 // (9,216 outputs, 148 partials) were a 15 us chain of dependent loads on 36 blocks.
 __global__ void __launch_bounds__(256) wgrad_reduce_klane_kernel(const float* __restrict__ ws, int ksplit, long long stride,
                                                                  float* __restrict__ dw, int Cout, int Cin, int taps) {
+  pdl_prologue();
   __shared__ float part[8][33];
   const int kl = threadIdx.x >> 5, li = threadIdx.x & 31;
   for (long long base = (long long)blockIdx.x * 32; base < stride; base += (long long)gridDim.x * 32) {
@@ -300,6 +303,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_klane_kernel(const float* __
 // partials (late stages: 0.6-2.4 M outputs, 12-48 partials = 28 MB that are still L2-resident).  Fixed summation order.
 __global__ void __launch_bounds__(256) wgrad_reduce_flat_kernel(const float* __restrict__ ws, int ksplit, long long stride,
                                                                 float* __restrict__ dw, int Cout, int Cin, int taps) {
+  pdl_prologue();
   const long long nv = stride >> 2;                   // Cin % 4 == 0 on this path
   for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < nv; iv += (long long)gridDim.x * blockDim.x) {
     const float4* src = reinterpret_cast<const float4*>(ws) + iv;
@@ -468,11 +472,11 @@ SVK_API int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* 
   const long long cap = (long long)svk_num_sms() * 8;
   if (ksplit >= 32 && stride <= 65536) {       // few outputs, many partials (stages 1-2): spread the k loop over 8 lanes
     long long b = (stride + 31) / 32; if (b > cap) b = cap;
-    wgrad_reduce_klane_kernel<<<(int)b, 256, 0, st>>>((const float*)workspace, ksplit, stride, dw_oihw, d->Cout, d->Cin, d->R * d->R);
+    svk_launch(wgrad_reduce_klane_kernel, (int)b, 256, 0, st, (const float*)workspace, ksplit, stride, dw_oihw, d->Cout, d->Cin, d->R * d->R);
   } else {
     SVK_REQUIRE(d->Cin % 4 == 0 && stride % 4 == 0, SVK_E_UNSUPPORTED, "conv2d_wgrad: Cin=%d must be a multiple of 4", d->Cin);
     long long b = (stride / 4 + 255) / 256; if (b > cap) b = cap;
-    wgrad_reduce_flat_kernel<<<(int)b, 256, 0, st>>>((const float*)workspace, ksplit, stride, dw_oihw, d->Cout, d->Cin, d->R * d->R);
+    svk_launch(wgrad_reduce_flat_kernel, (int)b, 256, 0, st, (const float*)workspace, ksplit, stride, dw_oihw, d->Cout, d->Cin, d->R * d->R);
   }
   SVK_LAUNCH_CHECK("conv2d_wgrad(reduce)");
   return 0;
@@ -489,6 +493,7 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
                                                        T* __restrict__ y, int N, int H, int W,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        int relu, const int* __restrict__ valid_w) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   constexpr int G = CO / V;                        // 16-byte pieces per output row
   constexpr int PITCH = G + 1;                     // odd pitch: conflict-free row writes
@@ -568,8 +573,8 @@ SVK_API int svk_stem_conv_fwd(const float* x, const float* w, void* y, int N, in
   long long b = (total + 127) / 128; long long cap = (long long)svk_num_sms() * 16; if (b > cap) b = cap;
   cudaStream_t st = as_stream(stream);
   SVK_DISPATCH_DTYPE(dtype, "stem_conv_fwd",
-    if (Cout == 32) stem_fwd_kernel<T, 32><<<(int)b, 128, 0, st>>>(x, w, (T*)y, N, H, W, scale, shift, relu, valid_w);
-    else stem_fwd_kernel<T, 64><<<(int)b, 128, 0, st>>>(x, w, (T*)y, N, H, W, scale, shift, relu, valid_w);)
+    if (Cout == 32) svk_launch(stem_fwd_kernel<T, 32>, (int)b, 128, 0, st, x, w, (T*)y, N, H, W, scale, shift, relu, valid_w);
+    else svk_launch(stem_fwd_kernel<T, 64>, (int)b, 128, 0, st, x, w, (T*)y, N, H, W, scale, shift, relu, valid_w);)
   SVK_LAUNCH_CHECK("stem_conv_fwd");
   return 0;
 }
@@ -580,6 +585,7 @@ SVK_API int svk_stem_conv_fwd(const float* x, const float* w, void* y, int N, in
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                          float* __restrict__ dw, int N, int H, int W, int CO) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   const int groups = CO / V;                                  // channel groups per pixel (4 or 8 for bf16)
   const int cg = threadIdx.x % groups, lane_p = threadIdx.x / groups, lanes = blockDim.x / groups;
@@ -628,7 +634,7 @@ SVK_API int svk_stem_conv_wgrad(const float* x, const void* dy, float* dw, int N
   int lanes = 256 / (Cout / (dtype == SVK_BF16 ? 8 : 4));
   long long b = (total + lanes * 16 - 1) / (lanes * 16); long long cap = (long long)svk_num_sms() * 2; if (b > cap) b = cap; if (b < 1) b = 1;
   SVK_DISPATCH_DTYPE(dtype, "stem_conv_wgrad",
-    stem_wgrad_kernel<T><<<(int)b, 256, 0, st>>>(x, (const T*)dy, dw, N, H, W, Cout);)
+    svk_launch(stem_wgrad_kernel<T>, (int)b, 256, 0, st, x, (const T*)dy, dw, N, H, W, Cout);)
   SVK_LAUNCH_CHECK("stem_conv_wgrad");
   return 0;
 }

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(SVK_GATHER_BOUNDS(BN), 1)
 conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ GatherP p) {
   typedef GatherCfg<KC, BN> Cfg;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -59,15 +60,16 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, tempty_count); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();             // everything above overlapped the previous kernel's tail; global memory is touched from here on
   if (p.scale) {
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
   }
   if (p.bn_c) {
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.bn_mean[i]; coef[512 + i] = p.bn_rstd[i]; }
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(Cfg::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -218,6 +220,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SVK_GATHER_BOUNDS(BN
 conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ GatherP p) {
   typedef Gather2Cfg<KC, BN> Cfg;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -237,15 +240,16 @@ conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * per_cta); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();             // everything above overlapped the previous kernel's tail; global memory is touched from here on
   if (p.scale) {
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
   }
   if (p.bn_c) {
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.bn_mean[i]; coef[512 + i] = p.bn_rstd[i]; }
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(Cfg::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -363,6 +367,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   constexpr int ROWB = CK * 2;
   constexpr uint32_t LAYOUT = (CK == 64) ? 2u : 4u;
   constexpr uint32_t SBO = 8 * ROWB;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -392,6 +397,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -536,7 +542,7 @@ int launch_gather_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP&
   }
   int grid = p.total_tiles < svk_num_sms() ? p.total_tiles : svk_num_sms();
   // 8 epilogue warps for narrow tiles (their epilogue outlasts their MMAs) and for the fused BatchNorm-backward epilogue
-  conv_tc_gather_kernel<KC, BN><<<grid, (BN <= 64 || p.bn_mask) ? GATHER_THREADS : TC_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
+  svk_launch(conv_tc_gather_kernel<KC, BN>, grid, (BN <= 64 || p.bn_mask) ? GATHER_THREADS : TC_THREADS, Cfg::SMEM, st, ta, tb, p);
   SVK_LAUNCH_CHECK("conv_tc_gather");
   return 0;
 }
@@ -568,7 +574,7 @@ int launch_gather2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GatherP
     if (getenv("SVK_VERBOSE")) fprintf(stderr, "svk: conv_tc_gather2<%d,%d> threads %d: %d resident CTA pairs\n", KC, BN, threads, nc);
   }
   const int grid = 2 * (n_pairs < mp ? n_pairs : mp);
-  conv_tc_gather2_kernel<KC, BN><<<grid, threads, Cfg::SMEM, st>>>(ta, tb, p);
+  svk_launch(conv_tc_gather2_kernel<KC, BN>, grid, threads, Cfg::SMEM, st, ta, tb, p);
   SVK_LAUNCH_CHECK("conv_tc_gather2");
   return 0;
 }
@@ -839,12 +845,12 @@ int svk_conv2d_wgrad_tc(const svk_conv_desc* d, const void* x, const void* dy, f
     static bool cfg64 = false;
     if (!cfg64) { cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); cfg64 = true; }
-    conv_tc_wgrad_kernel<64><<<grid, TC_THREADS, smem, st>>>(tdy, tx, p);
+    svk_launch(conv_tc_wgrad_kernel<64>, grid, TC_THREADS, smem, st, tdy, tx, p);
   } else {
     static bool cfg32 = false;
     if (!cfg32) { cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); cfg32 = true; }
-    conv_tc_wgrad_kernel<32><<<grid, TC_THREADS, smem, st>>>(tdy, tx, p);
+    svk_launch(conv_tc_wgrad_kernel<32>, grid, TC_THREADS, smem, st, tdy, tx, p);
   }
   SVK_LAUNCH_CHECK("conv_tc_wgrad");
   *ksplit_out = p.ksplit;

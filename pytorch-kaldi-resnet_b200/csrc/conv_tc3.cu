@@ -41,6 +41,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+  pdl_launch_dependents();
   const GatherP& p = q.g;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -68,15 +69,16 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int a = 0; a < 4; ++a) mbar_init(bar_afull + 8 * a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();             // everything above overlapped the previous kernel's tail; global memory is touched from here on
   if (p.scale) {
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.scale[i]; coef[512 + i] = p.shift[i]; }
   }
   if (p.bn_c) {
     for (int i = threadIdx.x; i < p.Nout; i += blockDim.x) { coef[i] = p.bn_mean[i]; coef[512 + i] = p.bn_rstd[i]; }
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -222,7 +224,7 @@ int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tx,
     configured = true;
   }
   int grid = q.g.total_tiles < svk_num_sms() ? q.g.total_tiles : svk_num_sms();
-  conv_tc_gather3_kernel<KC, BN, DGRAD><<<grid, GATHER_THREADS, smem, st>>>(ta, tb, tx[0], tx[1], tx[2], tx[3], q);
+  svk_launch(conv_tc_gather3_kernel<KC, BN, DGRAD>, grid, GATHER_THREADS, smem, st, ta, tb, tx[0], tx[1], tx[2], tx[3], q);
   SVK_LAUNCH_CHECK("conv_tc_gather3");
   return 0;
 }

@@ -43,6 +43,7 @@ conv_tc_wgrad9_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr int MMAS = (CK == 32) ? 1 : 2;            // UMMAs per K step
   constexpr int ACC_COLS = 3 * CK;                    // one accumulator = 128 lanes x 3C columns
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -67,6 +68,7 @@ conv_tc_wgrad9_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();             // the prologue above overlapped the previous kernel's tail; global memory is touched from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -227,12 +229,12 @@ int svk_conv2d_wgrad9_tc(const svk_conv_desc* d, const void* x, const void* dy, 
     static bool cfg = false;
     if (!cfg) { cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad9_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, W9_SMEM_MAX);
       SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); cfg = true; }
-    conv_tc_wgrad9_kernel<64><<<p.ksplit, TC_THREADS, smem, st>>>(tdy, tx, p);
+    svk_launch(conv_tc_wgrad9_kernel<64>, p.ksplit, TC_THREADS, smem, st, tdy, tx, p);
   } else {
     static bool cfg = false;
     if (!cfg) { cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad9_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, W9_SMEM_MAX);
       SVK_REQUIRE(e == cudaSuccess, (int)e, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); cfg = true; }
-    conv_tc_wgrad9_kernel<32><<<p.ksplit, TC_THREADS, smem, st>>>(tdy, tx, p);
+    svk_launch(conv_tc_wgrad9_kernel<32>, p.ksplit, TC_THREADS, smem, st, tdy, tx, p);
   }
   SVK_LAUNCH_CHECK("conv_tc_wgrad9");
   *ksplit_out = p.ksplit;

@@ -38,6 +38,7 @@ conv_tc_wgradr_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
   constexpr uint32_t LAYOUT = 2u;                     // SWIZZLE_128B
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr int ACC_COLS = 192;                       // one accumulator = 128 Cout x (3 taps x 64 Cin)
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -65,6 +66,7 @@ conv_tc_wgradr_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();             // the prologue above overlapped the previous kernel's tail; global memory is touched from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -233,7 +235,7 @@ int svk_conv2d_wgradr_tc(const svk_conv_desc* d, const void* x, const void* dy, 
     cfg = true;
   }
   const int grid = (d->Cout / 128) * p.n_n_blk * 3 * p.ksplit;
-  conv_tc_wgradr_kernel<<<grid, TC_THREADS, smem, st>>>(tdy, tx, p);
+  svk_launch(conv_tc_wgradr_kernel, grid, TC_THREADS, smem, st, tdy, tx, p);
   SVK_LAUNCH_CHECK("conv_tc_wgradr");
   *ksplit_out = p.ksplit;
   return 0;

@@ -17,6 +17,7 @@ static inline bool pow2(int c) { return c > 0 && (c & (c - 1)) == 0; }
 template <typename T>
 __global__ void pack_w_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cout, int Cin,
                               int taps) {
+  pdl_prologue();
   long long n = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int t = (int)(i % taps);
@@ -32,7 +33,7 @@ SVK_API int svk_pack_conv_weight(const float* w, void* wf, void* wd, int Cout, i
   SVK_REQUIRE(w && (wf || wd) && Cout > 0 && Cin > 0 && (R == 1 || R == 3), SVK_E_BADARG, "pack_conv_weight: bad args");
   long long n = (long long)Cout * Cin * R * R;
   SVK_DISPATCH_DTYPE(dtype, "pack_conv_weight",
-    pack_w_kernel<T><<<ew_grid(n), EW_THREADS, 0, as_stream(stream)>>>(w, (T*)wf, (T*)wd, Cout, Cin, R * R);)
+    svk_launch(pack_w_kernel<T>, ew_grid(n), EW_THREADS, 0, as_stream(stream), w, (T*)wf, (T*)wd, Cout, Cin, R * R);)
   SVK_LAUNCH_CHECK("pack_conv_weight");
   return 0;
 }
@@ -71,6 +72,7 @@ __device__ inline void channel_reduce(long long M, int C, double* __restrict__ s
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) channel_stats_kernel(const T* __restrict__ x, long long M, int C,
                                                                   double* __restrict__ stats) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   channel_reduce<T, 2>(M, C, stats, [&](long long off, int, float (&acc)[2][V]) {
     float v[V];
@@ -97,7 +99,7 @@ SVK_API int svk_channel_stats(const void* x, long long M, int C, int dtype, doub
   SVK_REQUIRE(x && stats, SVK_E_BADARG, "channel_stats: null pointer");
   if (int e = check_mc("channel_stats", M, C, dtype)) return e;
   SVK_DISPATCH_DTYPE(dtype, "channel_stats",
-    channel_stats_kernel<T><<<red_grid(M, C, Vec<T>::N), EW_THREADS, 0, as_stream(stream)>>>((const T*)x, M, C, stats);)
+    svk_launch(channel_stats_kernel<T>, red_grid(M, C, Vec<T>::N), EW_THREADS, 0, as_stream(stream), (const T*)x, M, C, stats);)
   SVK_LAUNCH_CHECK("channel_stats");
   return 0;
 }
@@ -106,6 +108,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, long long M
                                    const float* __restrict__ beta, float* __restrict__ rm, float* __restrict__ rv,
                                    float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double mean = stats[c] / (double)M;
@@ -127,7 +130,7 @@ SVK_API int svk_bn_finalize(const double* stats, long long M, int C, const float
                             float* rv, float momentum, float eps, float* scale, float* shift, float* save_mean,
                             float* save_rstd, void* stream) {
   SVK_REQUIRE(stats && gamma && beta && scale && shift && M > 0 && C > 0, SVK_E_BADARG, "bn_finalize: bad args");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(stats, M, C, gamma, beta, rm, rv, momentum, eps,
+  svk_launch(bn_finalize_kernel, (C + 127) / 128, 128, 0, as_stream(stream), stats, M, C, gamma, beta, rm, rv, momentum, eps,
                                                                     scale, shift, save_mean, save_rstd);
   SVK_LAUNCH_CHECK("bn_finalize");
   return 0;
@@ -135,6 +138,7 @@ SVK_API int svk_bn_finalize(const double* stats, long long M, int C, const float
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
                                       float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float sc = gamma[c] / sqrtf(rv[c] + eps);
@@ -144,7 +148,7 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
 SVK_API int svk_bn_eval_coeffs(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
                                int C, float* scale, float* shift, void* stream) {
   SVK_REQUIRE(gamma && beta && rm && rv && scale && shift && C > 0, SVK_E_BADARG, "bn_eval_coeffs: bad args");
-  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, rm, rv, eps, C, scale, shift);
+  svk_launch(bn_eval_coeffs_kernel, (C + 127) / 128, 128, 0, as_stream(stream), gamma, beta, rm, rv, eps, C, scale, shift);
   SVK_LAUNCH_CHECK("bn_eval_coeffs");
   return 0;
 }
@@ -156,6 +160,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 bn_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                   const T* __restrict__ res, const float* __restrict__ rscale, const float* __restrict__ rshift,
                   int relu, T* __restrict__ out, long long nvec, int C) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   const int lanes_c = C / V;
   long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,9 +193,9 @@ SVK_API int svk_bn_act_fwd(const void* x, const float* scale, const float* shift
   SVK_DISPATCH_DTYPE(dtype, "bn_act_fwd",
     long long nvec = M * C / Vec<T>::N;
     int g = ew_grid(nvec);
-    if (!res) bn_act_fwd_kernel<T, 0><<<g, EW_THREADS, 0, as_stream(stream)>>>((const T*)x, scale, shift, nullptr, nullptr, nullptr, relu, (T*)out, nvec, C);
-    else if (!rscale) bn_act_fwd_kernel<T, 1><<<g, EW_THREADS, 0, as_stream(stream)>>>((const T*)x, scale, shift, (const T*)res, nullptr, nullptr, relu, (T*)out, nvec, C);
-    else bn_act_fwd_kernel<T, 2><<<g, EW_THREADS, 0, as_stream(stream)>>>((const T*)x, scale, shift, (const T*)res, rscale, rshift, relu, (T*)out, nvec, C);)
+    if (!res) svk_launch(bn_act_fwd_kernel<T, 0>, g, EW_THREADS, 0, as_stream(stream), (const T*)x, scale, shift, nullptr, nullptr, nullptr, relu, (T*)out, nvec, C);
+    else if (!rscale) svk_launch(bn_act_fwd_kernel<T, 1>, g, EW_THREADS, 0, as_stream(stream), (const T*)x, scale, shift, (const T*)res, nullptr, nullptr, relu, (T*)out, nvec, C);
+    else svk_launch(bn_act_fwd_kernel<T, 2>, g, EW_THREADS, 0, as_stream(stream), (const T*)x, scale, shift, (const T*)res, rscale, rshift, relu, (T*)out, nvec, C);)
   SVK_LAUNCH_CHECK("bn_act_fwd");
   return 0;
 }
@@ -202,6 +207,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
                      const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ cb,
                      const float* __restrict__ meanb, const float* __restrict__ rstdb, double* __restrict__ sums,
                      long long M, int C) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   constexpr int NACC = TWO ? 3 : 2;
   channel_reduce<T, NACC>(M, C, sums, [&](long long off, int c0, float (&acc)[NACC][V]) {
@@ -224,7 +230,7 @@ static void launch_bn_bwd_reduce(const void* dout, const void* out, const void* 
                                  const void* cb, const float* meanb, const float* rstdb, double* sums, long long M, int C,
                                  cudaStream_t s) {
   int g = red_grid(M, C, Vec<T>::N);
-#define SVK_BR(MASK_, TWO_) bn_bwd_reduce_kernel<T, MASK_, TWO_><<<g, EW_THREADS, 0, s>>>((const T*)dout, (const T*)out, (const T*)c, mean, rstd, (const T*)cb, meanb, rstdb, sums, M, C)
+#define SVK_BR(MASK_, TWO_) svk_launch(bn_bwd_reduce_kernel<T, MASK_, TWO_>, g, EW_THREADS, 0, s, (const T*)dout, (const T*)out, (const T*)c, mean, rstd, (const T*)cb, meanb, rstdb, sums, M, C)
   if (out && cb) SVK_BR(true, true); else if (out) SVK_BR(true, false); else if (cb) SVK_BR(false, true); else SVK_BR(false, false);
 #undef SVK_BR
 }
@@ -248,6 +254,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
                     const float* __restrict__ rstdb, const float* __restrict__ gammab, T* __restrict__ dcb,
                     const double* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     float* __restrict__ dgammab, float* __restrict__ dbetab, long long nvec, long long M, int C) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   extern __shared__ float s_k[];             // [10][C]: mu, rs, k0, k1, k2 and the same for the second BN
   const int lanes_c = C / V;
@@ -314,7 +321,7 @@ static void launch_bn_bwd_apply(const void* dout, const void* out, const void* c
   long long nvec = M * C / Vec<T>::N;
   int g = ew_grid(nvec);
   const size_t sm = (size_t)(cb ? 10 : 5) * C * sizeof(float);
-#define SVK_BA(MASK_, TWO_) bn_bwd_apply_kernel<T, MASK_, TWO_><<<g, EW_THREADS, sm, s>>>((const T*)dout, (const T*)out, (const T*)c, mean, rstd, gamma, (T*)dc, (const T*)cb, meanb, rstdb, gammab, (T*)dcb, sums, dgamma, dbeta, dgammab, dbetab, nvec, M, C)
+#define SVK_BA(MASK_, TWO_) svk_launch(bn_bwd_apply_kernel<T, MASK_, TWO_>, g, EW_THREADS, sm, s, (const T*)dout, (const T*)out, (const T*)c, mean, rstd, gamma, (T*)dc, (const T*)cb, meanb, rstdb, gammab, (T*)dcb, sums, dgamma, dbeta, dgammab, dbetab, nvec, M, C)
   if (out && cb) SVK_BA(true, true); else if (out) SVK_BA(true, false); else if (cb) SVK_BA(false, true); else SVK_BA(false, false);
 #undef SVK_BA
 }
@@ -337,6 +344,7 @@ template <typename T, bool MASK>
 __global__ void __launch_bounds__(EW_THREADS)
 add_masked_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ mask, T* __restrict__ out,
                   long long nvec) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (long long)gridDim.x * blockDim.x) {
     float x[V], y[V], m[V];
@@ -353,14 +361,15 @@ SVK_API int svk_add_masked(const void* a, const void* b, const void* mask, void*
   SVK_DISPATCH_DTYPE(dtype, "add_masked",
     SVK_REQUIRE(n % Vec<T>::N == 0, SVK_E_ALIGN, "add_masked: n=%lld not a multiple of %d", n, Vec<T>::N);
     long long nvec = n / Vec<T>::N;
-    if (mask) add_masked_kernel<T, true><<<ew_grid(nvec), EW_THREADS, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (const T*)mask, (T*)out, nvec);
-    else add_masked_kernel<T, false><<<ew_grid(nvec), EW_THREADS, 0, as_stream(stream)>>>((const T*)a, (const T*)b, nullptr, (T*)out, nvec);)
+    if (mask) svk_launch(add_masked_kernel<T, true>, ew_grid(nvec), EW_THREADS, 0, as_stream(stream), (const T*)a, (const T*)b, (const T*)mask, (T*)out, nvec);
+    else svk_launch(add_masked_kernel<T, false>, ew_grid(nvec), EW_THREADS, 0, as_stream(stream), (const T*)a, (const T*)b, nullptr, (T*)out, nvec);)
   SVK_LAUNCH_CHECK("add_masked");
   return 0;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) relu_mask_kernel(T* __restrict__ g, const T* __restrict__ mask, long long nvec) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (long long)gridDim.x * blockDim.x) {
     float x[V], m[V];
@@ -376,7 +385,7 @@ SVK_API int svk_relu_mask_inplace(void* g, const void* mask, long long n, int dt
   SVK_DISPATCH_DTYPE(dtype, "relu_mask_inplace",
     SVK_REQUIRE(n % Vec<T>::N == 0, SVK_E_ALIGN, "relu_mask_inplace: n=%lld not a multiple of %d", n, Vec<T>::N);
     long long nvec = n / Vec<T>::N;
-    relu_mask_kernel<T><<<ew_grid(nvec), EW_THREADS, 0, as_stream(stream)>>>((T*)g, (const T*)mask, nvec);)
+    svk_launch(relu_mask_kernel<T>, ew_grid(nvec), EW_THREADS, 0, as_stream(stream), (T*)g, (const T*)mask, nvec);)
   SVK_LAUNCH_CHECK("relu_mask_inplace");
   return 0;
 }
@@ -384,6 +393,7 @@ SVK_API int svk_relu_mask_inplace(void* g, const void* mask, long long n, int dt
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
 add_strided2_kernel(T* __restrict__ dx, const T* __restrict__ d, int N, int H, int W, int Ho, int Wo, int C) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   const int lanes_c = C / V;
   long long nvec = (long long)N * Ho * Wo * lanes_c;
@@ -407,7 +417,7 @@ SVK_API int svk_add_strided2(void* dx, const void* d, int N, int H, int W, int H
   if (int e = check_mc("add_strided2", 1, C, dtype)) return e;
   SVK_DISPATCH_DTYPE(dtype, "add_strided2",
     long long nvec = (long long)N * Ho * Wo * (C / Vec<T>::N);
-    add_strided2_kernel<T><<<ew_grid(nvec), EW_THREADS, 0, as_stream(stream)>>>((T*)dx, (const T*)d, N, H, W, Ho, Wo, C);)
+    svk_launch(add_strided2_kernel<T>, ew_grid(nvec), EW_THREADS, 0, as_stream(stream), (T*)dx, (const T*)d, N, H, W, Ho, Wo, C);)
   SVK_LAUNCH_CHECK("add_strided2");
   return 0;
 }
@@ -416,6 +426,7 @@ SVK_API int svk_add_strided2(void* dx, const void* d, int N, int H, int W, int H
 __global__ void __launch_bounds__(EW_THREADS)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n, float lr,
            float mom, float wd, float gscale) {
+  pdl_prologue();
   long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pv = reinterpret_cast<float4*>(p)[i], gv = reinterpret_cast<const float4*>(g)[i], bv = reinterpret_cast<float4*>(buf)[i];
@@ -441,13 +452,14 @@ SVK_API int svk_sgd_step(float* p, const float* g, float* buf, long long n, floa
                          float gscale, void* stream) {
   SVK_REQUIRE(p && g && buf && n > 0, SVK_E_BADARG, "sgd_step: bad args");
   SVK_REQUIRE(aligned16(p) && aligned16(g) && aligned16(buf), SVK_E_ALIGN, "sgd_step: buffers must be 16-byte aligned");
-  sgd_kernel<<<ew_grid(n / 4 + 1), EW_THREADS, 0, as_stream(stream)>>>(p, g, buf, n, lr, momentum, wd, gscale);
+  svk_launch(sgd_kernel, ew_grid(n / 4 + 1), EW_THREADS, 0, as_stream(stream), p, g, buf, n, lr, momentum, wd, gscale);
   SVK_LAUNCH_CHECK("sgd_step");
   return 0;
 }
 
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, long long n) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     d[i] = from_f<D>(to_f(s[i]));
 }
@@ -455,10 +467,10 @@ SVK_API int svk_cast(const void* src, void* dst, long long n, int sd, int dd, vo
   SVK_REQUIRE(src && dst && n > 0, SVK_E_BADARG, "cast: bad args");
   int g = ew_grid(n);
   cudaStream_t s = as_stream(stream);
-  if (sd == SVK_F32 && dd == SVK_BF16) cast_kernel<<<g, EW_THREADS, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n);
-  else if (sd == SVK_BF16 && dd == SVK_F32) cast_kernel<<<g, EW_THREADS, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
-  else if (sd == SVK_F32 && dd == SVK_F32) cast_kernel<<<g, EW_THREADS, 0, s>>>((const float*)src, (float*)dst, n);
-  else if (sd == SVK_BF16 && dd == SVK_BF16) cast_kernel<<<g, EW_THREADS, 0, s>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  if (sd == SVK_F32 && dd == SVK_BF16) svk_launch(cast_kernel<float, __nv_bfloat16>, g, EW_THREADS, 0, s, (const float*)src, (__nv_bfloat16*)dst, n);
+  else if (sd == SVK_BF16 && dd == SVK_F32) svk_launch(cast_kernel<__nv_bfloat16, float>, g, EW_THREADS, 0, s, (const __nv_bfloat16*)src, (float*)dst, n);
+  else if (sd == SVK_F32 && dd == SVK_F32) svk_launch(cast_kernel<float, float>, g, EW_THREADS, 0, s, (const float*)src, (float*)dst, n);
+  else if (sd == SVK_BF16 && dd == SVK_BF16) svk_launch(cast_kernel<__nv_bfloat16, __nv_bfloat16>, g, EW_THREADS, 0, s, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
   else { svk_set_error("cast: bad dtypes %d -> %d", sd, dd); return SVK_E_BADARG; }
   SVK_LAUNCH_CHECK("cast");
   return 0;
@@ -474,6 +486,7 @@ template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
 pack_all_kernel(const float* __restrict__ flat, T* __restrict__ wf, T* __restrict__ wd, const long long* __restrict__ table,
                 int nconv) {
+  pdl_prologue();
   __shared__ float tile[32 * (32 * 9 + 1)];
   __shared__ int s_first[65];                 // first unit of conv k (nconv <= 64), s_first[nconv] = number of units
   if (threadIdx.x < nconv)      // tile count of conv k (one round trip for the whole table), then an exclusive scan
@@ -520,7 +533,7 @@ SVK_API int svk_pack_conv_weights_batched(const float* flat, void* wf, void* wd,
   // one block per 32x32 tile when there are few, a grid-stride over them otherwise (taps >= 1: total/1024 bounds the count)
   long long nb = total / 1024 + nconv; long long cap = (long long)svk_num_sms() * 6; if (nb > cap) nb = cap;
   SVK_DISPATCH_DTYPE(dtype, "pack_conv_weights_batched",
-    pack_all_kernel<T><<<(int)nb, EW_THREADS, 0, as_stream(stream)>>>(flat, (T*)wf, (T*)wd, table, nconv);)
+    svk_launch(pack_all_kernel<T>, (int)nb, EW_THREADS, 0, as_stream(stream), flat, (T*)wf, (T*)wd, table, nconv);)
   SVK_LAUNCH_CHECK("pack_conv_weights_batched");
   return 0;
 }
@@ -560,6 +573,7 @@ template <typename T, int RES /*0 none, 1 plain, 2 second BN*/>
 __global__ void __launch_bounds__(EW_THREADS)
 bn_train_act_kernel(const T* __restrict__ x, BnTrainArgs a, const T* __restrict__ res, BnTrainArgs b, float momentum,
                     float eps, int relu, T* __restrict__ out, long long nvec, long long M, int C, int cstride) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   extern __shared__ float s_coef[];          // [4][C]: scale, shift, (second BN) scale, shift
   const int lanes_c = C / V;
@@ -602,9 +616,9 @@ SVK_API int svk_bn_train_act_fwd(const void* x, const double* stats, const float
     int g = ew_grid(nvec);
     cudaStream_t s = as_stream(stream);
     const size_t sm = (size_t)4 * C * sizeof(float);
-    if (!res) bn_train_act_kernel<T, 0><<<g, EW_THREADS, sm, s>>>((const T*)x, a, nullptr, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);
-    else if (!stats_b) bn_train_act_kernel<T, 1><<<g, EW_THREADS, sm, s>>>((const T*)x, a, (const T*)res, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);
-    else bn_train_act_kernel<T, 2><<<g, EW_THREADS, sm, s>>>((const T*)x, a, (const T*)res, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);)
+    if (!res) svk_launch(bn_train_act_kernel<T, 0>, g, EW_THREADS, sm, s, (const T*)x, a, nullptr, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);
+    else if (!stats_b) svk_launch(bn_train_act_kernel<T, 1>, g, EW_THREADS, sm, s, (const T*)x, a, (const T*)res, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);
+    else svk_launch(bn_train_act_kernel<T, 2>, g, EW_THREADS, sm, s, (const T*)x, a, (const T*)res, b, momentum, eps, relu, (T*)out, nvec, M, C, cstride);)
   SVK_LAUNCH_CHECK("bn_train_act_fwd");
   return 0;
 }

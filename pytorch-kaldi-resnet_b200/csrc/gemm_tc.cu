@@ -39,6 +39,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, i
 template <bool AK, bool BK_>   // operand stored K-major?
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmP p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -55,6 +56,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(128) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();             // the prologue above overlapped the previous kernel's tail; global memory is touched from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -150,6 +152,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 __global__ void __launch_bounds__(256) gemm_reduce_kernel(const float* __restrict__ part, int ksplit, long long stride,
                                                           float* __restrict__ C, long long ldc, long long ldp, int M, int N,
                                                           const float* __restrict__ bias) {
+  pdl_prologue();
   long long total = (long long)M * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int n = (int)(i % N); long long m = i / N;
@@ -185,7 +188,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP& p, in
     SVK_REQUIRE(e == cudaSuccess, (int)e, "gemm_tf32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     configured = true;
   }
-  gemm_tf32_kernel<AK, BK_><<<grid, TC_THREADS, G_SMEM, st>>>(ta, tb, p);
+  svk_launch(gemm_tf32_kernel<AK, BK_>, grid, TC_THREADS, G_SMEM, st, ta, tb, p);
   SVK_LAUNCH_CHECK("gemm_tf32");
   return 0;
 }
@@ -244,7 +247,7 @@ SVK_API int svk_gemm_tf32(const float* A, long long lda, int a_kmajor, const flo
   if (p.ksplit > 1) {
     long long total = (long long)M * N;
     long long b = (total + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
-    gemm_reduce_kernel<<<(int)b, 256, 0, st>>>((const float*)workspace, p.ksplit, p.part_stride, C, ldc, ldp, M, N, bias);
+    svk_launch(gemm_reduce_kernel, (int)b, 256, 0, st, (const float*)workspace, p.ksplit, p.part_stride, C, ldc, ldp, M, N, bias);
     SVK_LAUNCH_CHECK("gemm_tf32(reduce)");
   }
   return 0;

@@ -9,6 +9,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) statspool_fwd_kernel(const T* __restrict__ x, float* __restrict__ out, int N,
                                                             int H, int W, int C, int mode,
                                                             const int* __restrict__ valid_w) {
+  pdl_prologue();
   long long total = (long long)N * H * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C); long long q = i / C; int h = (int)(q % H); int n = (int)(q / H);
@@ -34,7 +35,7 @@ SVK_API int svk_statspool_fwd(const void* x, float* out, int N, int H, int W, in
   long long total = (long long)N * H * C;
   long long b = (total + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
   SVK_DISPATCH_DTYPE(dtype, "statspool_fwd",
-    statspool_fwd_kernel<T><<<(int)b, 256, 0, as_stream(stream)>>>((const T*)x, out, N, H, W, C, mode, valid_w);)
+    svk_launch(statspool_fwd_kernel<T>, (int)b, 256, 0, as_stream(stream), (const T*)x, out, N, H, W, C, mode, valid_w);)
   SVK_LAUNCH_CHECK("statspool_fwd");
   return 0;
 }
@@ -47,6 +48,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) statspool_bwd_kernel(const T* __restrict__ x, const float* __restrict__ dout,
                                                             T* __restrict__ dx, int N, int H, int W, int C, int mode,
                                                             int relu_mask) {
+  pdl_prologue();
   long long total = (long long)N * H * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C); long long q = i / C; int h = (int)(q % H); int n = (int)(q / H);
@@ -76,7 +78,7 @@ SVK_API int svk_statspool_bwd(const void* x, const float* dout, void* dx, int N,
   long long total = (long long)N * H * C;
   long long b = (total + 255) / 256; long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap;
   SVK_DISPATCH_DTYPE(dtype, "statspool_bwd",
-    statspool_bwd_kernel<T><<<(int)b, 256, 0, as_stream(stream)>>>((const T*)x, dout, (T*)dx, N, H, W, C, mode, relu_mask);)
+    svk_launch(statspool_bwd_kernel<T>, (int)b, 256, 0, as_stream(stream), (const T*)x, dout, (T*)dx, N, H, W, C, mode, relu_mask);)
   SVK_LAUNCH_CHECK("statspool_bwd");
   return 0;
 }
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(const float* __restrict__ A, 
                                                    const float* __restrict__ B, long long b_sk, long long b_sn,
                                                    float* __restrict__ C, long long ldc, int M, int N, int K,
                                                    float alpha, float beta, const float* __restrict__ bias) {
+  pdl_prologue();
   __shared__ float As[GK][GM + 4];
   __shared__ float Bs[GK][GN + 4];
   const int t = threadIdx.x;
@@ -159,15 +162,16 @@ SVK_API int svk_sgemm(const float* A, long long a_sm, long long a_sk, const floa
   dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
   cudaStream_t st = as_stream(stream);
   bool ak = (a_sk == 1), bk = (b_sk == 1);
-  if (ak && bk) sgemm_kernel<true, true><<<grid, GT, 0, st>>>(A, a_sm, a_sk, B, b_sk, b_sn, C, ldc, M, N, K, alpha, beta, bias);
-  else if (ak) sgemm_kernel<true, false><<<grid, GT, 0, st>>>(A, a_sm, a_sk, B, b_sk, b_sn, C, ldc, M, N, K, alpha, beta, bias);
-  else if (bk) sgemm_kernel<false, true><<<grid, GT, 0, st>>>(A, a_sm, a_sk, B, b_sk, b_sn, C, ldc, M, N, K, alpha, beta, bias);
-  else sgemm_kernel<false, false><<<grid, GT, 0, st>>>(A, a_sm, a_sk, B, b_sk, b_sn, C, ldc, M, N, K, alpha, beta, bias);
+  if (ak && bk) svk_launch(sgemm_kernel<true, true>, grid, GT, 0, st, A, a_sm, a_sk, B, b_sk, b_sn, C, ldc, M, N, K, alpha, beta, bias);
+  else if (ak) svk_launch(sgemm_kernel<true, false>, grid, GT, 0, st, A, a_sm, a_sk, B, b_sk, b_sn, C, ldc, M, N, K, alpha, beta, bias);
+  else if (bk) svk_launch(sgemm_kernel<false, true>, grid, GT, 0, st, A, a_sm, a_sk, B, b_sk, b_sn, C, ldc, M, N, K, alpha, beta, bias);
+  else svk_launch(sgemm_kernel<false, false>, grid, GT, 0, st, A, a_sm, a_sk, B, b_sk, b_sn, C, ldc, M, N, K, alpha, beta, bias);
   SVK_LAUNCH_CHECK("sgemm");
   return 0;
 }
 
 __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, long long ld) {
+  pdl_prologue();
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -176,7 +180,7 @@ __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ o
 }
 SVK_API int svk_colsum(const float* x, float* out, int M, int N, long long ld, void* stream) {
   SVK_REQUIRE(x && out && M > 0 && N > 0 && ld >= N, SVK_E_BADARG, "colsum: bad args");
-  colsum_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(x, out, M, N, ld);
+  svk_launch(colsum_kernel, (N + 127) / 128, 128, 0, as_stream(stream), x, out, M, N, ld);
   SVK_LAUNCH_CHECK("colsum");
   return 0;
 }

@@ -32,6 +32,57 @@ void svk_count_launch(int n = 1);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ----------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched with the programmatic-stream-serialization
+// attribute: it may START (be scheduled, run its prologue: barrier init, TMEM allocation, tensor-map prefetch) while the
+// previous kernel of the stream is still draining, and it calls pdl_wait() — which returns once that kernel has completed
+// and its memory is visible — before its first access to global memory.  pdl_launch_dependents() at the top of a kernel
+// lets the NEXT kernel's blocks be scheduled as soon as all blocks of this one have started.  The training step is ~250
+// back-to-back kernels of 20-150 us; the ~2.5 us launch gap between two of them (profiles/r02_timeline_before_pdl.json:
+// 0.58 ms of a 9.4 ms step) is what this hides.  RULE: every __global__ function calls pdl_wait() unconditionally, in
+// every block, before touching global memory — a kernel that skipped it could finish before its predecessor and release
+// ITS successor too early.  SVK_DISABLE_PDL=1 launches without the attribute (the device-side calls are then no-ops).
+// WHERE the trigger goes matters (measured on one box, bench.py --steps 30, ms per step; profiles/r02_pdl.md):
+//     no PDL 9.37 | no explicit trigger (dependents start when the last block EXITS) 9.12 | tensor-core kernels trigger at
+//     their start 9.48 | every kernel triggers at its start 9.52.
+// An early trigger makes the next kernel's blocks resident while this one runs; a waiting tensor-core CTA (200 KB of smem,
+// its TMEM columns) keeps the side stream's weight-gradient CTAs off that SM, and those are meant to run beside the
+// elementwise passes.  So nothing triggers early: the gain is the launch latency + memory flush that the pre-staged
+// dependent skips, with the prologue above pdl_wait() overlapping it.  The macros keep the other placements buildable
+// (csrc/build.py --variant NAME -DSVK_PDL_TC_EARLY=1).
+#ifndef SVK_PDL_EW_EARLY
+#define SVK_PDL_EW_EARLY 0
+#endif
+#ifndef SVK_PDL_TC_EARLY
+#define SVK_PDL_TC_EARLY 0
+#endif
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {      // tensor-core kernels
+#if SVK_PDL_TC_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_prologue() {               // elementwise / reduction kernels: no prologue worth overlapping
+#if SVK_PDL_EW_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+  pdl_wait();
+}
+
+bool svk_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline void svk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = svk_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // the caller checks cudaGetLastError (SVK_LAUNCH_CHECK)
+}
+
 static inline int svk_num_sms() {
   static int n = 0;
   if (n == 0) {

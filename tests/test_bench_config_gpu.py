@@ -171,7 +171,6 @@ def _bench_model(precision):
 def _step(m, x, y):
     from svk.loss import CrossEntropyLoss
     m.train()
-    m.engine.debug = {}
     logits = m(x, y)
     loss = CrossEntropyLoss()(logits, y)
     loss.backward()
