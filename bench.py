@@ -218,8 +218,7 @@ def run_ours(args):
     model.train()
 
     def step(x, y):
-        out = model(x, y)
-        loss = crit(out, y)
+        loss, out = model.forward_loss(x, y)     # = model(x, y) + CrossEntropyLoss, what scripts/train_resnet.py::train calls
         opt.zero_grad()
         loss.backward()
         opt.step()

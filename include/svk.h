@@ -212,6 +212,22 @@ int svk_ce_fwd(const float* logits, const long long* label, float* loss_rows, fl
 int svk_ce_bwd(const float* logits, const long long* label, const float* lse, const float* gout, float mult,
                float* dlogits, int B, int C, void* stream);
 
+/* Fused AAM-softmax head + cross-entropy (csrc/aam_fused.cu), embedding width E = 256 only.
+ * replaces: AAMLayer.forward (model.py:483-501) + nn.CrossEntropyLoss (train_resnet.py:201,317) + accuracy.py:4-16 and
+ * their autograd backward, in four launches; d_logits, x_hat and W_hat never exist in memory.
+ *   fwd: logits[B,C] (margin on the target column, x s), cos_t[B] (raw target cosine), lse[B], loss_rows[B] (nullable),
+ *        rank[B] (nullable; classes scoring strictly above the target), loss_mean (nullable; zeroed, then += loss_rows/B).
+ *   bwd: dh[B,E], dW[C,E] from (logits, lse, cos_t) and the upstream scalar *gout (nullable = 1): d loss_mean.
+ *   exact != 0: 3xTF32 split products (fp32 validation mode, <= 1e-5 of the fp32 oracle); 0: single tf32 products.
+ *   workspace: svk_aam_ce_workspace_bytes(B, E, C) bytes, 16-byte aligned; the same buffer serves fwd and bwd. */
+size_t svk_aam_ce_workspace_bytes(int B, int E, int C);
+int svk_aam_ce_fwd(const float* h, const float* W, const long long* label, float* logits, float* cos_t, float* lse,
+                   float* loss_rows, int* rank, float* loss_mean, int B, int E, int C, float cos_m, float sin_m, float th,
+                   float mm, float s, int exact, void* workspace, size_t workspace_bytes, void* stream);
+int svk_aam_ce_bwd(const float* h, const float* W, const long long* label, const float* logits, const float* lse,
+                   const float* cos_t, const float* gout, float* dh, float* dW, int B, int E, int C, float cos_m, float sin_m,
+                   float th, float s, int exact, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- optimiser ------------------------------ */
 /* torch.optim.SGD semantics on flat buffers: d = g*gscale + wd*p; buf = mom*buf + d; p -= lr*buf.
  * (buf zero-initialised makes the first step equal torch's buf = d.)  replaces: train_resnet.py:203,328. */

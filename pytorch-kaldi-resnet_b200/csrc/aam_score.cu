@@ -222,16 +222,15 @@ __device__ inline float key2f(unsigned k) {
   unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
   return __uint_as_float(u);
 }
-__global__ void __launch_bounds__(256) topk_meanstd_kernel(const float* __restrict__ scores, int ncoh, int topk,
-                                                           float* __restrict__ mean, float* __restrict__ stdv) {
-  pdl_prologue();
+// General path: 3-level radix select (11 + 11 + 10 bits) + one summation pass — any k, any value distribution.
+__device__ void topk_radix_row(const float* __restrict__ p, int ncoh, int topk, float* __restrict__ mean_out,
+                               float* __restrict__ std_out) {
   __shared__ int hist[2048];
   __shared__ int part[256];
   __shared__ unsigned s_prefix;
   __shared__ int s_k;
   __shared__ double s_sum[8], s_sq[8];
   __shared__ int s_cnt[8];
-  const float* p = scores + (long long)blockIdx.x * ncoh;
   const int t = threadIdx.x;
   if (t == 0) { s_prefix = 0u; s_k = topk; }
   const int shifts[3] = {21, 10, 0};
@@ -298,6 +297,72 @@ __global__ void __launch_bounds__(256) topk_meanstd_kernel(const float* __restri
     for (int w = 0; w < 8; ++w) { S += s_sum[w]; Q += s_sq[w]; }
     S += (double)n_eq * vth; Q += (double)n_eq * vth * vth;
     double m = S / topk;
+    double var = (Q - S * m) / (double)(topk - 1);
+    if (var < 0.0) var = 0.0;
+    *mean_out = (float)m;
+    *std_out = (float)sqrt(var);
+  }
+}
+
+// Fast path for k <= 512 of a long row (the s-norm case: top-300 of 50,000 cosines).  The radix select above reads the row
+// four times and funnels every element of a clustered distribution through a handful of shared-memory histogram bins;
+// here the row is read twice and almost nothing is atomic:
+//   1. every thread keeps the two largest keys of its strided slice (512 keys, all of them elements of the row);
+//   2. tau = the k-th largest of those 512 (rank by counting, broadcast smem reads): a LOWER bound of the true k-th largest;
+//   3. second pass: the elements >= tau are the only candidates (k <= count, typically ~1.3 k) -> smem list;
+//   4. exact rank of every candidate inside the list (ties broken by list position), fp64 sums of ranks < k.
+// A row whose candidate list overflows (adversarial data) takes the radix path.
+constexpr int TK_SLOTS = 512, TK_CAND = 2048;
+__global__ void __launch_bounds__(256) topk_meanstd_kernel(const float* __restrict__ scores, int ncoh, int topk,
+                                                           float* __restrict__ mean, float* __restrict__ stdv) {
+  pdl_prologue();
+  const float* p = scores + (long long)blockIdx.x * ncoh;
+  if (topk > TK_SLOTS || ncoh < 4 * TK_SLOTS) { topk_radix_row(p, ncoh, topk, mean + blockIdx.x, stdv + blockIdx.x); return; }
+  __shared__ unsigned slot[TK_SLOTS];
+  __shared__ unsigned cand[TK_CAND];
+  __shared__ unsigned s_tau;
+  __shared__ int s_n;
+  __shared__ double r_sum[8], r_sq[8];
+  const int t = threadIdx.x;
+  unsigned k1 = 0u, k2 = 0u;                   // two largest keys of this thread's slice (key 0 sorts below every float)
+  for (int i = t; i < ncoh; i += 256) {
+    const unsigned k = f2key(p[i]);
+    if (k > k1) { k2 = k1; k1 = k; } else if (k > k2) k2 = k;
+  }
+  slot[t] = k1; slot[256 + t] = k2;
+  if (t == 0) s_n = 0;
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int me = h * 256 + t;
+    const unsigned k = slot[me];
+    int rank = 0;
+    for (int j = 0; j < TK_SLOTS; ++j) { const unsigned o = slot[j]; rank += (o > k || (o == k && j < me)) ? 1 : 0; }
+    if (rank == topk - 1) s_tau = k;
+  }
+  __syncthreads();
+  const unsigned tau = s_tau;
+  for (int i = t; i < ncoh; i += 256) {
+    const unsigned k = f2key(p[i]);
+    if (k >= tau) { const int pos = atomicAdd(&s_n, 1); if (pos < TK_CAND) cand[pos] = k; }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n > TK_CAND) { topk_radix_row(p, ncoh, topk, mean + blockIdx.x, stdv + blockIdx.x); return; }      // uniform per block
+  double sum = 0.0, sq = 0.0;
+  for (int me = t; me < n; me += 256) {
+    const unsigned k = cand[me];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) { const unsigned o = cand[j]; rank += (o > k || (o == k && j < me)) ? 1 : 0; }
+    if (rank < topk) { const double v = (double)key2f(k); sum += v; sq += v * v; }
+  }
+  for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+  if ((t & 31) == 0) { r_sum[t >> 5] = sum; r_sq[t >> 5] = sq; }
+  __syncthreads();
+  if (t == 0) {
+    double S = 0.0, Q = 0.0;
+    for (int w = 0; w < 8; ++w) { S += r_sum[w]; Q += r_sq[w]; }
+    const double m = S / topk;
     double var = (Q - S * m) / (double)(topk - 1);
     if (var < 0.0) var = 0.0;
     mean[blockIdx.x] = (float)m;

@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(os.path.dirname(HERE), "svk")
-SOURCES = ["svk_api.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc3.cu", "conv_tc_wgrad9.cu", "conv_tc_wgradr.cu", "pool_gemm.cu", "gemm_tc.cu", "aam_score.cu", "backend.cu"]
+SOURCES = ["svk_api.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc3.cu", "conv_tc_wgrad9.cu", "conv_tc_wgradr.cu", "pool_gemm.cu", "gemm_tc.cu", "aam_score.cu", "aam_fused.cu", "backend.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--extended-lambda", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
 

@@ -169,6 +169,21 @@ class NeuralSpeakerModel(nn.Module):
         with torch.no_grad():
             return self._engine.forward_eval(x, y=y, with_head=True)
 
+    def forward_loss(self, x, y):
+        """model(x, y) and CrossEntropyLoss()(logits, y) in one call (train_resnet.py:316-317): -> (mean loss, logits).
+        AAM heads run the fused AAM-softmax-cross-entropy kernels (the backward starts from d loss: no (B, C) gradient is
+        ever materialised) and attach the target ranks to the logits (`logits.svk_rank`, what accuracy() needs); the
+        softmax head composes the two calls.  Training mode only; beyond the reference API."""
+        self._check_input(x)
+        if self.training and self.loss != "softmax" and self._engine.fused_head:
+            from svk import ops
+            loss, logits, rank = ops.speaker_net_train_loss(self._engine, x, y)
+            logits.svk_rank = rank
+            return loss, logits
+        from svk.loss import CrossEntropyLoss
+        logits = self(x, y)
+        return CrossEntropyLoss()(logits, y), logits
+
     def predict(self, x, lengths=None):
         """(B, F, T) -> (B, 256) embeddings = fc1 output (model.py:402-409).  `lengths` (optional, beyond the
         reference API) gives per-row valid frame counts for zero-padded batches of different-length utterances."""

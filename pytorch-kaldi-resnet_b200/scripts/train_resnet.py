@@ -254,8 +254,9 @@ def train(train_loader, model, criterion, optimizer, epoch, args):
     # compute stream)
     for i, (audios, target) in enumerate(DevicePrefetcher(train_loader, torch.device('cuda', args.gpu))):
         dt = time.time() - end
-        output = model(audios, target)
-        loss = criterion(output, target)
+        # model(audios, target) + criterion(output, target) (train_resnet.py:316-317) as one call: AAM heads run the fused
+        # AAM-softmax-cross-entropy kernels and hand back the target ranks accuracy() needs
+        loss, output = model.forward_loss(audios, target)
         meters.update(loss, target_rank(output, target), audios.size(0))
         optimizer.zero_grad()
         loss.backward()

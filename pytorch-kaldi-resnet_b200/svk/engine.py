@@ -97,6 +97,8 @@ class SpeakerNetEngine(object):
         # test hook: delay every side-stream weight gradient by this many GPU cycles, so that a missing stream dependency
         # (the main stream overwriting a buffer the side stream still reads) produces wrong gradients deterministically
         self._side_delay = int(os.environ.get("SVK_WGRAD_STREAM_DELAY_CYCLES", "0"))
+        self.fused_head = os.environ.get("SVK_DISABLE_FUSED_HEAD", "0") != "1"     # A/B switch: csrc/aam_fused.cu vs ~17 small launches
+        self.last_head = None           # {"loss", "rank"} of the most recent fused AAM head forward
         self.debug_masked = set()       # debug taps that hold the gradient already multiplied by the ReLU mask
         self.debug = None               # tests set this to a dict to capture per-layer gradients (clones)
         self._index_modules()
@@ -455,24 +457,47 @@ class SpeakerNetEngine(object):
             if y is None:
                 raise lib.SvkError("AAM head needs labels: call model(x, y)")
             y = y.contiguous()
-            xh = self._buf(ws, "aam_xh", (B, E), torch.float32)
-            xinv = self._buf(ws, "aam_xinv", (B,), torch.float32)
-            wh = self._buf(ws, "aam_wh", (C, E), torch.float32)
-            winv = self._buf(ws, "aam_winv", (C,), torch.float32)
-            cos_t = self._buf(ws, "aam_cos_t", (B,), torch.float32)
-            call.svk_l2norm_rows_fwd(h.data_ptr(), xh.data_ptr(), xinv.data_ptr(), B, E, 1e-12, st)
-            call.svk_l2norm_rows_fwd(last.weight.data_ptr(), wh.data_ptr(), winv.data_ptr(), C, E, 1e-12, st)
-            self._gemm(xh, E, True, wh, E, True, logits, C, B, C, E)
-            call.svk_aam_margin_fwd(logits.data_ptr(), y.data_ptr(), cos_t.data_ptr(), B, C, last.cos_m, last.sin_m,
-                                    last.th, last.mm, float(last.s), st)
-            if sv is not None:
-                sv.update(y=y, xh=xh, xinv=xinv, wh=wh, winv=winv, cos_t=cos_t)
+            if E == 256 and self.fused_head:
+                # ONE fused pass (csrc/aam_fused.cu): row normalisation, cosine GEMM, margin, scale, log-sum-exp, loss, rank
+                need = lib.load().svk_aam_ce_workspace_bytes(B, E, C)
+                hws = self._arena("aam_ws", ((need + 3) // 4,), torch.float32)
+                cos_t = self._buf(ws, "aam_cos_t", (B,), torch.float32)
+                lse = self._buf(ws, "aam_lse", (B,), torch.float32)
+                rank = torch.empty(B, dtype=torch.int32, device=self.device)
+                loss_mean = torch.empty((), dtype=torch.float32, device=self.device)
+                call.svk_aam_ce_fwd(h.data_ptr(), last.weight.data_ptr(), y.data_ptr(), logits.data_ptr(), cos_t.data_ptr(),
+                                    lse.data_ptr(), 0, rank.data_ptr(), loss_mean.data_ptr(), B, E, C, last.cos_m, last.sin_m,
+                                    last.th, last.mm, float(last.s), 1 if self.precision == "fp32" else 0, hws.data_ptr(),
+                                    hws.numel() * 4, st)
+                self.last_head = {"loss": loss_mean, "rank": rank}
+                if sv is not None:
+                    sv.update(y=y, cos_t=cos_t, lse=lse, logits=logits, fused=True)
+            else:
+                xh, xinv, wh, winv = self._aam_normalise(h, last.weight, ws, B, E, C)
+                cos_t = self._buf(ws, "aam_cos_t", (B,), torch.float32)
+                self._gemm(xh, E, True, wh, E, True, logits, C, B, C, E)
+                call.svk_aam_margin_fwd(logits.data_ptr(), y.data_ptr(), cos_t.data_ptr(), B, C, last.cos_m, last.sin_m,
+                                        last.th, last.mm, float(last.s), st)
+                self.last_head = None
+                if sv is not None:
+                    sv.update(y=y, xh=xh, xinv=xinv, wh=wh, winv=winv, cos_t=cos_t, fused=False)
         if sv is not None:
             sv.update(h=h, C=C)
         return logits
 
-    def _head_bwd(self, dlogits, sv):
-        """dlogits (B, C) fp32 (consumed in place) -> d emb (B, E); writes head parameter gradients."""
+    def _aam_normalise(self, h, weight, ws, B, E, C):
+        st = _stream()
+        xh = self._buf(ws, "aam_xh", (B, E), torch.float32)
+        xinv = self._buf(ws, "aam_xinv", (B,), torch.float32)
+        wh = self._buf(ws, "aam_wh", (C, E), torch.float32)
+        winv = self._buf(ws, "aam_winv", (C,), torch.float32)
+        call.svk_l2norm_rows_fwd(h.data_ptr(), xh.data_ptr(), xinv.data_ptr(), B, E, 1e-12, st)
+        call.svk_l2norm_rows_fwd(weight.data_ptr(), wh.data_ptr(), winv.data_ptr(), C, E, 1e-12, st)
+        return xh, xinv, wh, winv
+
+    def _head_bwd(self, dlogits, sv, dloss=None):
+        """d emb (B, E) from the upstream gradient; writes the head's parameter gradients.  Either dlogits (B, C) fp32
+        (consumed in place), or — fused loss path — dloss, the scalar gradient of the mean cross-entropy."""
         model = self.model
         st = _stream()
         ws = sv["ws"]
@@ -481,21 +506,34 @@ class SpeakerNetEngine(object):
         last = model.last
         gw = self._gview[id(last.weight)]
         h = sv["h"]
-        Cp = dlogits.stride(0)                  # padded row pitch of the upstream-gradient copy
         dh = self._buf(ws, "d_h", (B, E), torch.float32)
-        if loss == "softmax":
+        if dloss is not None:
+            # fused backward (csrc/aam_fused.cu): d_logits recomputed from the logits + lse, both normalisation Jacobians inside
+            need = lib.load().svk_aam_ce_workspace_bytes(B, E, C)
+            hws = self._arena("aam_ws", ((need + 3) // 4,), torch.float32)
+            call.svk_aam_ce_bwd(h.data_ptr(), last.weight.data_ptr(), sv["y"].data_ptr(), sv["logits"].data_ptr(),
+                                sv["lse"].data_ptr(), sv["cos_t"].data_ptr(), dloss.data_ptr(), dh.data_ptr(), gw.data_ptr(), B, E, C,
+                                last.cos_m, last.sin_m, last.th, float(last.s), 1 if self.precision == "fp32" else 0,
+                                hws.data_ptr(), hws.numel() * 4, st)
+        elif loss == "softmax":
+            Cp = dlogits.stride(0)                  # padded row pitch of the upstream-gradient copy
             self._gemm(dlogits, Cp, True, last.weight, E, False, dh, E, B, E, C)           # dh = dlogits * W
             self._gemm(dlogits, Cp, False, h, E, False, gw, E, C, E, B)                    # dW = dlogits^T * h
             call.svk_colsum(dlogits.data_ptr(), self._gview[id(last.bias)].data_ptr(), B, C, Cp, st)
         else:
+            Cp = dlogits.stride(0)
+            if sv.get("fused"):                     # the fused forward kept no normalised copies: rebuild them
+                xh, xinv, wh, winv = self._aam_normalise(h, last.weight, ws, B, E, C)
+            else:
+                xh, xinv, wh, winv = sv["xh"], sv["xinv"], sv["wh"], sv["winv"]
             call.svk_aam_margin_bwd(dlogits.data_ptr(), sv["y"].data_ptr(), sv["cos_t"].data_ptr(), B, C, Cp, last.cos_m,
                                     last.sin_m, last.th, float(last.s), st)
             dxh = self._buf(ws, "d_xh", (B, E), torch.float32)
             dwh = self._buf(ws, "d_wh", (C, E), torch.float32)
-            self._gemm(dlogits, Cp, True, sv["wh"], E, False, dxh, E, B, E, C)             # dx_hat = dcos * W_hat
-            self._gemm(dlogits, Cp, False, sv["xh"], E, False, dwh, E, C, E, B)            # dW_hat = dcos^T * x_hat
-            call.svk_l2norm_rows_bwd(dxh.data_ptr(), sv["xh"].data_ptr(), sv["xinv"].data_ptr(), dh.data_ptr(), B, E, st)
-            call.svk_l2norm_rows_bwd(dwh.data_ptr(), sv["wh"].data_ptr(), sv["winv"].data_ptr(), gw.data_ptr(), C, E, st)
+            self._gemm(dlogits, Cp, True, wh, E, False, dxh, E, B, E, C)                   # dx_hat = dcos * W_hat
+            self._gemm(dlogits, Cp, False, xh, E, False, dwh, E, C, E, B)                  # dW_hat = dcos^T * x_hat
+            call.svk_l2norm_rows_bwd(dxh.data_ptr(), xh.data_ptr(), xinv.data_ptr(), dh.data_ptr(), B, E, st)
+            call.svk_l2norm_rows_bwd(dwh.data_ptr(), wh.data_ptr(), winv.data_ptr(), gw.data_ptr(), C, E, st)
         if loss in ("softmax", "AAM-v1"):
             bn = self.head_bn
             sc, sh, mu, rs = self._coefs(bn)
@@ -512,8 +550,9 @@ class SpeakerNetEngine(object):
         return dh
 
     # ------------------------------------------------------------------------------------------ training backward
-    def backward_train(self, dlogits, sv):
-        """Backward of the forward that produced `sv`.  Parameter gradients are WRITTEN into the flat gradient buffer
+    def backward_train(self, dlogits, sv, dloss=None):
+        """Backward of the forward that produced `sv`: from dlogits (B, C), or (fused loss path) from dloss, the scalar
+        gradient of the mean cross-entropy the fused head computed.  Parameter gradients are WRITTEN into the flat gradient buffer
         (p.grad views); when the previous backward's gradients were not consumed by SGD.step() / zero_grad() they are
         added on top, which is torch's accumulation semantics (the reference zeroes them every step, train_resnet.py:326)."""
         if sv is None or sv.get("done"):
@@ -529,16 +568,20 @@ class SpeakerNetEngine(object):
         ws = sv["ws"]
         B = sv["B"]
         self._bsums.zero_()
-        # private copy of the upstream gradient (the head backward works in place) with a row pitch that is a multiple of
-        # 4 floats, so the tensor-core GEMMs can map it with TMA
-        Bq, Cq = dlogits.shape
-        Cp = (Cq + 3) // 4 * 4
-        pad = self._buf(ws, "d_logits_pad", (Bq, Cp), torch.float32)
-        pad[:, :Cq].copy_(dlogits)
-        if Cp != Cq:
-            pad[:, Cq:].zero_()
-        dlogits = pad[:, :Cq]
-        demb = self._head_bwd(dlogits, sv)
+        if dloss is not None:
+            if not sv.get("fused"):
+                raise lib.SvkError("the fused loss backward needs the fused AAM head forward")
+            demb = self._head_bwd(None, sv, dloss=dloss.contiguous().float())
+        else:
+            # private copy of the upstream gradient (the head backward works in place) with a row pitch that is a multiple
+            # of 4 floats, so the tensor-core GEMMs can map it with TMA
+            Bq, Cq = dlogits.shape
+            Cp = (Cq + 3) // 4 * 4
+            pad = self._buf(ws, "d_logits_pad", (Bq, Cp), torch.float32)
+            pad[:, :Cq].copy_(dlogits)
+            if Cp != Cq:
+                pad[:, Cq:].zero_()
+            demb = self._head_bwd(pad[:, :Cq], sv)
         # ---- fc1
         fc = model.fc1
         pdim, E = sv["pdim"], sv["E"]

@@ -61,6 +61,8 @@ SIGNATURES = {
     "svk_l2norm_rows_bwd": [_P, _P, _P, _P, _I, _I, _P],
     "svk_aam_margin_fwd": [_P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _P],
     "svk_aam_margin_bwd": [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _P],
+    "svk_aam_ce_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _F, _I, _P, ctypes.c_size_t, _P],
+    "svk_aam_ce_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _I, _P, ctypes.c_size_t, _P],
     "svk_gemm_tf32": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _P, _P, ctypes.c_size_t, _P],
     "svk_ce_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     "svk_ce_bwd": [_P, _P, _P, _P, _F, _P, _I, _I, _P],
@@ -98,6 +100,8 @@ def load():
     lib.svk_conv2d_wgrad_workspace_bytes.argtypes = [_D]
     lib.svk_gemm_tf32_workspace_bytes.restype = ctypes.c_size_t
     lib.svk_gemm_tf32_workspace_bytes.argtypes = [_I, _I, _I]
+    lib.svk_aam_ce_workspace_bytes.restype = ctypes.c_size_t
+    lib.svk_aam_ce_workspace_bytes.argtypes = [_I, _I, _I]
     for name, argtypes in (("svk_sort_pairs_f64_workspace_bytes", [_L]), ("svk_det_metrics_workspace_bytes", [_L]),
                            ("svk_col_mean_workspace_bytes", [_L, _I])):
         getattr(lib, name).restype = ctypes.c_size_t

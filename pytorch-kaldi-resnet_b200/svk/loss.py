@@ -20,6 +20,9 @@ class CrossEntropyLoss(nn.Module):
 
 def target_rank(logits, target):
     """rank[b] = number of classes scoring strictly above the target class (0 = top-1 hit)."""
+    rank = getattr(logits, "svk_rank", None)        # already computed by the fused AAM head (model.forward_loss)
+    if rank is not None:
+        return rank
     _check(logits)
     return torch.ops.svk.target_rank(logits.detach().contiguous(), target.contiguous().long())
 

@@ -8,6 +8,7 @@ CUDA only — there is no CPU kernel behind any of them (no fallback), a CPU ten
 
     op                                   replaces (reference)                       C-ABI behind it
     svk::speaker_net_train (+_backward)  NeuralSpeakerModel.forward, model.py:374   the whole plan of svk/engine.py
+    svk::speaker_net_train_loss (+_bwd)  forward + CrossEntropyLoss (:316-317)      same, with the fused AAM-softmax-CE head
     svk::speaker_net_embed               NeuralSpeakerModel.predict, model.py:402   eval plan (BatchNorm folded)
     svk::cross_entropy (+_backward)      nn.CrossEntropyLoss, train_resnet.py:201   svk_ce_fwd / svk_ce_bwd
     svk::target_rank                     accuracy(), accuracy.py:4-16               svk_ce_fwd (rank output)
@@ -126,6 +127,68 @@ def speaker_net_train(engine, x, y):
     save = torch.is_grad_enabled() and any(p.requires_grad for p in engine._params)
     logits, _ = torch.ops.svk.speaker_net_train(x, y, list(engine._params), engine_handle(engine), save)
     return logits
+
+
+# ---- the same network with the cross-entropy INSIDE the head (fused AAM-softmax-CE, csrc/aam_fused.cu): returns the mean loss,
+# the margin logits and the target ranks; its backward starts from d loss (a scalar), so d_logits never exists in memory.
+@custom_op("svk::speaker_net_train_loss", mutates_args=(), device_types="cuda")
+def _speaker_net_train_loss(x: Tensor, y: Tensor, params: List[Tensor], handle: int, save: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """(B, F, T) fp32, (B,) int64 -> (mean cross-entropy (), logits (B, C), rank (B,) int32, token).  AAM heads only."""
+    eng = _engine(handle)
+    logits, sv = eng.forward_train(x, y, save=save)
+    head = eng.last_head
+    if head is None:
+        raise lib.SvkError("svk::speaker_net_train_loss needs the fused AAM head (loss 'AAM' / 'AAM-v1', 256-d embeddings)")
+    tok = eng._next_token = getattr(eng, "_next_token", 0) + 1
+    if save:
+        eng._pending = getattr(eng, "_pending", {})
+        eng._pending[tok] = sv
+    return head["loss"], logits, head["rank"], torch.tensor(tok, dtype=torch.int64)
+
+
+@register_fake("svk::speaker_net_train_loss")
+def _(x, y, params, handle, save):
+    C = _engine(handle).model.last.weight.shape[0]
+    B = x.shape[0]
+    return (x.new_empty((), dtype=torch.float32), x.new_empty((B, C), dtype=torch.float32),
+            x.new_empty((B,), dtype=torch.int32), torch.empty((), dtype=torch.int64))
+
+
+@custom_op("svk::speaker_net_train_loss_backward", mutates_args={"flat_grads"}, device_types="cuda")
+def _speaker_net_train_loss_backward(dloss: Tensor, flat_grads: Tensor, handle: int, token: int) -> None:
+    eng = _engine(handle)
+    sv = getattr(eng, "_pending", {}).pop(token, None)
+    eng.backward_train(None, sv, dloss=dloss)
+
+
+def _train_loss_setup(ctx, inputs, output):
+    x, y, params, handle, save = inputs
+    ctx.handle = handle
+    ctx.token = int(output[3])
+    ctx.nparams = len(params)
+    ctx.guard = _PendingGuard(handle, ctx.token)
+    ctx.set_materialize_grads(False)
+
+
+def _train_loss_backward(ctx, dloss, dlogits, drank, dtoken):
+    if dlogits is not None:
+        raise lib.SvkError("svk::speaker_net_train_loss: a gradient arrived through the logits; use model(x, y) + "
+                           "CrossEntropyLoss when the logits feed another differentiable term")
+    if dloss is not None:
+        eng = _engine(ctx.handle)
+        torch.ops.svk.speaker_net_train_loss_backward(dloss, eng.flat_grads, ctx.handle, ctx.token)
+    return None, None, [None] * ctx.nparams, None, None
+
+
+register_autograd("svk::speaker_net_train_loss", _train_loss_backward, setup_context=_train_loss_setup)
+
+
+def speaker_net_train_loss(engine, x, y):
+    """-> (loss, logits, rank); loss carries the autograd node."""
+    engine.ensure_device()
+    save = torch.is_grad_enabled() and any(p.requires_grad for p in engine._params)
+    loss, logits, rank, _ = torch.ops.svk.speaker_net_train_loss(x, y, list(engine._params), engine_handle(engine), save)
+    return loss, logits, rank
 
 
 @custom_op("svk::speaker_net_embed", mutates_args=(), device_types="cuda")
@@ -338,5 +401,6 @@ def _(scores, idx_enroll, idx_test, mean_e, std_e, mean_t, std_t):
     return torch.empty_like(scores)
 
 
-REGISTERED = ("speaker_net_train", "speaker_net_train_backward", "speaker_net_embed", "cross_entropy", "cross_entropy_backward",
+REGISTERED = ("speaker_net_train", "speaker_net_train_backward", "speaker_net_train_loss", "speaker_net_train_loss_backward",
+              "speaker_net_embed", "cross_entropy", "cross_entropy_backward",
               "target_rank", "sgd_step", "conv2d", "conv2d_backward", "cosine_score_pairs", "topk_meanstd", "snorm_apply")

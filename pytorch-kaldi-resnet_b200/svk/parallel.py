@@ -97,6 +97,9 @@ class DistributedDataParallel(nn.Module):
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
 
+    def forward_loss(self, x, y):
+        return self.module.forward_loss(x, y)
+
 
 def shard_range(n, rank, world):
     """Contiguous, balanced [lo, hi) slice of n independent units for this rank (trial blocks, embedding rows)."""

@@ -43,25 +43,32 @@ def l2_normalize_rows(x, eps=1e-12):
     return out
 
 
-def cohort_topk_meanstd(vecs, cohort, topk=300, block_rows=4096, device="cuda", tf32=False):
+SCORE_BLOCK_ROWS = 4096      # measured (profiles/r02_snorm_blocks.md): 256-row blocks keep the score block in L2 but lose more
+                             # to launch / tail overhead (2.5 M rows/s) than 4,096-row blocks pay in HBM traffic (3.6 M rows/s)
+
+
+def cohort_topk_meanstd(vecs, cohort, topk=300, block_rows=None, device="cuda", tf32=False):
     """For every row v of `vecs`: scores = normalize(cohort) @ normalize(v); top-k; (mean, unbiased std).
     Both inputs must already be mean-subtracted (compute_topk_mean_std.py:41-48).  Returns (mean, std) tensors.
     tf32=True computes the score matrix on the tensor cores (tcgen05 kind::tf32; scores within ~2e-4 of fp32, inside
-    the 1e-3 north-star bound); the default keeps exact fp32 products like the reference."""
+    the 1e-3 north-star bound); the default keeps exact fp32 products like the reference.
+    The full (n, cohort) score matrix never exists: rows are processed in blocks of `block_rows` (default SCORE_BLOCK_ROWS),
+    written by the GEMM and read back twice by the select (thread-local top-2 -> threshold -> candidate list)."""
     X, Cm = _f32(vecs, device), _f32(cohort, device)
     n, D = X.shape
     nc = Cm.shape[0]
     if nc < topk:
         raise ValueError("cohort of %d rows is smaller than topk=%d (torch.topk would fail too)" % (nc, topk))
-    mean = torch.empty(n, dtype=torch.float32, device=device)
-    std = torch.empty(n, dtype=torch.float32, device=device)
     if n == 0:
-        return mean, std
+        return torch.empty(0, dtype=torch.float32, device=device), torch.empty(0, dtype=torch.float32, device=device)
     Cn = l2_normalize_rows(Cm)
     Xn = l2_normalize_rows(X)
+    if block_rows is None:
+        block_rows = SCORE_BLOCK_ROWS
     block_rows = max(1, min(block_rows, n))
     scores = torch.empty(block_rows, nc, dtype=torch.float32, device=device)
     st = _st()
+    means, stds = [], []
     for lo in range(0, n, block_rows):
         rows = min(block_rows, n - lo)
         xb = Xn[lo:lo + rows]
@@ -73,8 +80,10 @@ def cohort_topk_meanstd(vecs, cohort, topk=300, block_rows=4096, device="cuda", 
                                0 if ws is None else ws.data_ptr(), need, st)
         else:
             call.svk_sgemm(xb.data_ptr(), D, 1, Cn.data_ptr(), 1, D, scores.data_ptr(), nc, rows, nc, D, 1.0, 0.0, 0, st)
-        mean[lo:lo + rows], std[lo:lo + rows] = torch.ops.svk.topk_meanstd(scores[:rows], topk)
-    return mean, std
+        m, sd = torch.ops.svk.topk_meanstd(scores[:rows], topk)
+        means.append(m)
+        stds.append(sd)
+    return torch.cat(means), torch.cat(stds)
 
 
 def snorm_apply(scores, idx_enroll, idx_test, mean_e, std_e, mean_t, std_t, device="cuda"):

@@ -42,7 +42,7 @@ def main():
     net.train()
 
     def step():
-        loss = crit(net(x, y), y)
+        loss, _ = net.forward_loss(x, y)
         opt.zero_grad()
         loss.backward()
         opt.step()

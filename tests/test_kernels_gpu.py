@@ -631,3 +631,88 @@ def test_train_script_end_to_end_then_decode():
         assert r3.returncode == 0, r3.stderr[-2000:]
         emb = dict(kaldi_io.read_vec_flt_ark(os.path.join(d, "emb", "0")))
         assert len(emb) == n_spk * utts_per_spk and all(v.shape == (256,) and np.isfinite(v).all() for v in emb.values())
+
+
+# ------------------------------------------------------------------------------------------------ fused AAM-softmax head
+@pytest.mark.parametrize("B,C", [(256, 5994), (32, 1211), (37, 1211), (5, 64), (130, 200)])
+@pytest.mark.parametrize("exact", [1, 0])
+def test_fused_aam_softmax_cross_entropy(B, C, exact):
+    """svk_aam_ce_fwd / svk_aam_ce_bwd (4 launches) against the oracle's AAMLayer + cross-entropy and their autograd
+    (model.py:483-501, train_resnet.py:317, accuracy.py:4-16): logits, loss, log-sum-exp, target rank, d h, d W.
+    exact=1 (fp32 validation mode, 3xTF32 products): <= 1e-5; exact=0 (product mode, single tf32 products): <= 2e-3 on the
+    logits (tf32 rounding of unit vectors), gradients <= 2e-2 (the bf16 path's bound)."""
+    E, m, s = 256, 0.2, 30.0
+    g = torch.Generator().manual_seed(B * 7 + C)
+    h = torch.randn(B, E, generator=g) * 3.0
+    W = torch.randn(C, E, generator=g) * 0.05
+    y = torch.randint(0, C, (B,), generator=g)
+    # rows that hit the "cos - th <= 0" branch of the margin (cos = -0.995 < th = -0.980) and a large positive cosine (0.9);
+    # not +-1 exactly: sqrt(1 - cos^2) is ill-conditioned there and two fp32 implementations legitimately differ
+    for r, (a, b) in ((0, (-0.995, 0.0999)), (1 % B, (0.9, 0.436))):
+        w = W[y[r]] / W[y[r]].norm()
+        u = torch.randn(E, generator=g)
+        u = u - (u @ w) * w
+        h[r] = 5.0 * (a * w + b * u / u.norm())
+    hr, Wr = h.clone().double().requires_grad_(True), W.clone().double().requires_grad_(True)
+    ref_logits = O.aam_logits(hr, Wr, y, m, s)
+    ref_loss = O.cross_entropy(ref_logits, y)
+    gout = 0.37                                   # an upstream gradient other than 1
+    (ref_loss * gout).backward()
+    cos_m, sin_m, th, mm = O.aam_constants(m)
+    hd, Wd, yd = h.cuda(), W.cuda(), y.cuda()
+    need = lib.load().svk_aam_ce_workspace_bytes(B, E, C)
+    assert need > 0
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    logits = torch.full((B, C), float("nan"), device="cuda")
+    cos_t, lse, rows = [torch.full((B,), float("nan"), device="cuda") for _ in range(3)]
+    rank = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+    loss = torch.full((), float("nan"), device="cuda")
+    call.svk_aam_ce_fwd(hd.data_ptr(), Wd.data_ptr(), yd.data_ptr(), logits.data_ptr(), cos_t.data_ptr(), lse.data_ptr(),
+                        rows.data_ptr(), rank.data_ptr(), loss.data_ptr(), B, E, C, cos_m, sin_m, th, mm, s, exact, ws.data_ptr(),
+                        ws.numel(), util.st())
+    tol = 1e-5 if exact else 2e-3
+    assert not torch.isnan(logits).any()
+    assert util.rel_err(logits.cpu(), ref_logits.detach()) <= tol
+    assert abs(float(loss) - float(ref_loss)) <= tol * abs(float(ref_loss))
+    assert util.rel_err(lse.cpu(), torch.logsumexp(ref_logits.detach(), 1)) <= tol
+    assert util.rel_err(rows.cpu(), (torch.logsumexp(ref_logits.detach(), 1) - ref_logits.detach().gather(1, y.view(-1, 1))[:, 0])) <= max(tol, 1e-5) * 10
+    got_logits = logits.cpu().double()
+    assert torch.equal(rank.cpu().long(), (got_logits > got_logits.gather(1, y.view(-1, 1))).sum(1)), "rank of the stored logits"
+    if exact:
+        assert torch.equal(rank.cpu().long(), (ref_logits.detach() > ref_logits.detach().gather(1, y.view(-1, 1))).sum(1))
+    gd = torch.tensor(gout, device="cuda")
+    dh = torch.full((B, E), float("nan"), device="cuda")
+    dW = torch.full((C, E), float("nan"), device="cuda")
+    call.svk_aam_ce_bwd(hd.data_ptr(), Wd.data_ptr(), yd.data_ptr(), logits.data_ptr(), lse.data_ptr(), cos_t.data_ptr(),
+                        gd.data_ptr(), dh.data_ptr(), dW.data_ptr(), B, E, C, cos_m, sin_m, th, s, exact, ws.data_ptr(), ws.numel(),
+                        util.st())
+    # fp64 oracle: fp32 rounding of the margin derivative at cos = -0.995 (amplified ~100x by 1 / sqrt(1 - cos^2)) alone is ~1e-5
+    gtol = 3e-5 if exact else 2e-2
+    assert not torch.isnan(dh).any() and not torch.isnan(dW).any()
+    assert util.rel_err(dh.cpu(), hr.grad) <= gtol
+    assert util.rel_err(dW.cpu(), Wr.grad) <= gtol
+    dW2 = torch.empty_like(dW)
+    call.svk_aam_ce_bwd(hd.data_ptr(), Wd.data_ptr(), yd.data_ptr(), logits.data_ptr(), lse.data_ptr(), cos_t.data_ptr(),
+                        gd.data_ptr(), dh.data_ptr(), dW2.data_ptr(), B, E, C, cos_m, sin_m, th, s, exact, ws.data_ptr(), ws.numel(),
+                        util.st())
+    assert torch.equal(dW, dW2), "fused head backward is not deterministic"
+
+
+def test_topk_meanstd_candidate_path_and_radix_fallback():
+    """The top-k select has a fast path (k <= 512 on long rows: thread-local top-2 -> threshold -> candidate list) and the
+    radix path (any k; also taken when the candidate list overflows): both equal torch.topk + std_mean on clustered,
+    heavy-tie and adversarial rows."""
+    g = torch.Generator().manual_seed(3)
+    rows = [torch.randn(50000, generator=g) * 0.06,                       # cosine-like cluster
+            torch.round(torch.randn(50000, generator=g) * 4) / 4,         # heavy ties
+            torch.cat([torch.full((3000,), 0.5), torch.randn(47000, generator=g) * 0.01]),   # > 2048 candidates tie at the top
+            -torch.rand(50000, generator=g),                              # all negative
+            torch.linspace(-1, 1, 50000)]
+    S = torch.stack(rows).cuda()
+    for k in (300, 2, 512, 600):
+        mean = torch.empty(len(rows), device="cuda")
+        std = torch.empty(len(rows), device="cuda")
+        call.svk_topk_meanstd(S.data_ptr(), len(rows), 50000, k, mean.data_ptr(), std.data_ptr(), util.st())
+        top = S.double().cpu().topk(k, dim=1).values
+        assert util.rel_err(mean.cpu(), top.mean(1)) <= 1e-6, k
+        assert float((std.cpu().double() - top.std(1)).abs().max()) <= 1e-6, k

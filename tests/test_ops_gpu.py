@@ -117,3 +117,42 @@ def test_network_operator_is_reentrant_and_accumulates_like_torch():
     out.backward(retain_graph=True)
     with pytest.raises(RuntimeError):
         out.backward()
+
+
+@pytest.mark.parametrize("loss_type", ["AAM", "AAM-v1", "softmax"])
+def test_forward_loss_equals_model_plus_criterion(loss_type):
+    """model.forward_loss (fused AAM-softmax-CE head, svk::speaker_net_train_loss: backward starts from d loss) gives the
+    loss, logits, ranks and parameter gradients of model(x, y) + CrossEntropyLoss + backward (train_resnet.py:316-327)."""
+    from model import NeuralSpeakerModel
+    from svk.loss import CrossEntropyLoss, target_rank
+    from svk.optim import SGD
+    torch.manual_seed(5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = NeuralSpeakerModel(spk_num=301, feat_dim=40, pooling="mean+std", loss=loss_type, precision="fp32").cuda()
+    opt = SGD(m.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(6, 40, 56, generator=g).cuda()
+    y = torch.randint(0, 301, (6,), generator=g).cuda()
+    m.train()
+    opt.zero_grad()
+    logits_a = m(x, y)
+    loss_a = CrossEntropyLoss()(logits_a, y)
+    rank_a = target_rank(logits_a, y)
+    (loss_a * 0.5).backward()
+    torch.cuda.synchronize()
+    ga = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    opt.zero_grad()
+    loss_b, logits_b = m.forward_loss(x, y)
+    (loss_b * 0.5).backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * abs(float(loss_a))
+    assert util.rel_err(logits_b.cpu(), logits_a.detach().cpu()) <= 1e-5
+    assert torch.equal(target_rank(logits_b, y).cpu(), rank_a.cpu())
+    for n, p in m.named_parameters():
+        assert util.rel_err(p.grad.cpu(), ga[n].cpu()) <= 2e-5, n
+    if loss_type != "softmax":
+        assert m.engine.last_head is not None and hasattr(logits_b, "svk_rank")
+        from svk import launch_count
+        n0 = launch_count()
+        m.engine._head_fwd(m.engine._train_ws[(6, 40, 56)][0]["emb"], y, m.engine._train_ws[(6, 40, 56)][0], None, True)
+        assert launch_count() - n0 <= (2 if loss_type == "AAM" else 4), "fused head forward = 2 launches (+ BatchNorm1d for AAM-v1)"
