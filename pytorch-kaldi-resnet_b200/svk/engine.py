@@ -471,7 +471,8 @@ class SpeakerNetEngine(object):
                                     hws.numel() * 4, st)
                 self.last_head = {"loss": loss_mean, "rank": rank}
                 if sv is not None:
-                    sv.update(y=y, cos_t=cos_t, lse=lse, logits=logits, fused=True)
+                    # detach(): the returned tensor gets the autograd node, which owns this state — no reference cycle
+                    sv.update(y=y, cos_t=cos_t, lse=lse, logits=logits.detach(), fused=True)
             else:
                 xh, xinv, wh, winv = self._aam_normalise(h, last.weight, ws, B, E, C)
                 cos_t = self._buf(ws, "aam_cos_t", (B,), torch.float32)

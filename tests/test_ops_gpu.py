@@ -149,7 +149,10 @@ def test_forward_loss_equals_model_plus_criterion(loss_type):
     assert util.rel_err(logits_b.cpu(), logits_a.detach().cpu()) <= 1e-5
     assert torch.equal(target_rank(logits_b, y).cpu(), rank_a.cpu())
     for n, p in m.named_parameters():
-        assert util.rel_err(p.grad.cpu(), ga[n].cpu()) <= 2e-5, n
+        if float(ga[n].abs().max()) < 1e-6:      # fc1.bias under a BatchNorm head: the gradient is identically zero, both sides are rounding noise
+            assert float(p.grad.abs().max()) < 1e-6, n
+        else:
+            assert util.rel_err(p.grad.cpu(), ga[n].cpu()) <= 2e-5, n
     if loss_type != "softmax":
         assert m.engine.last_head is not None and hasattr(logits_b, "svk_rank")
         from svk import launch_count
