@@ -116,10 +116,12 @@ size_t svk_conv2d_wgrad_workspace_bytes(const svk_conv_desc* d);
 int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* dy, float* dw_oihw, void* workspace,
                      size_t workspace_bytes, void* stream);
 
-/* Stem: 3x3 s1 p1 conv, Cin = 1, x is the (B,F,T) fp32 feature tensor itself.  replaces: model.py:247-249. */
+/* Stem: 3x3 s1 p1 conv, Cin = 1, x is the (B,F,T) fp32 feature tensor itself.  replaces: model.py:247-249.
+ * stats (nullable): [2*Cout] doubles, += per-channel sum / sum of squares of the stored values (caller zeroes). */
 int svk_stem_conv_fwd(const float* x, const float* w /*[Cout][9]*/, void* y /*N,H,W,Cout*/, int N, int H, int W,
                       int Cout, int dtype, const float* scale, const float* shift, int relu,
-                      const int* valid_w /*nullable, per-utterance width: y[n,:,w>=valid_w[n],:] = 0*/, void* stream);
+                      const int* valid_w /*nullable, per-utterance width: y[n,:,w>=valid_w[n],:] = 0*/, double* stats,
+                      void* stream);
 int svk_stem_conv_wgrad(const float* x, const void* dy, float* dw /*[Cout][9], overwritten*/, int N, int H, int W,
                         int Cout, int dtype, void* stream);
 

@@ -483,142 +483,177 @@ SVK_API int svk_conv2d_wgrad(const svk_conv_desc* d, const void* x, const void* 
 }
 
 // ------------------------------------------------------------------------------------------------ stem (Cin = 1)
-// One thread per output pixel, all Cout (<= 64) channels in registers; HBM-bound: reads 4 B, writes 2*Cout B per pixel.
-// The filter sits in shared memory tap-major, so one 16-byte broadcast load feeds four FMAs.  A warp owns 32 consecutive
-// pixels = one contiguous run of 32*Cout outputs: the rows are staged in shared memory and written back as fully
-// coalesced 512-byte stores (with every lane storing its own row, each store instruction touched 32 half-written sectors
-// and the kernel ran at 21 % of the HBM roof).
-template <typename T, int CO>
-__global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                       T* __restrict__ y, int N, int H, int W,
-                                                       const float* __restrict__ scale, const float* __restrict__ shift,
-                                                       int relu, const int* __restrict__ valid_w) {
+// HBM-bound by construction: 4 B in, 2 * Cout B out per pixel (131 MB at batch 256).  Work item = (image row, run of 4
+// consecutive pixels, group of V channels = one 16-byte piece of each output row).  A thread keeps its 9 x V filter taps in
+// REGISTERS for the whole kernel (the first version re-read all 288 taps from shared memory for every pixel: LDS-bound,
+// 28 % of the HBM roof), fetches the 3 x 6 input window of its run with 18 independent loads issued up front (a one-pixel
+// item with 9 dependent loads was latency-bound at 16 warps per SM), and consecutive threads write consecutive 16-byte
+// pieces.  Training forward: the per-channel sum / sum of squares of the values AS STORED are accumulated on the way (the
+// separate svk_channel_stats pass re-read the whole tensor).
+constexpr int STEM_RUN = 4;
+template <typename T, bool AFFINE, bool STATS>
+__global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          T* __restrict__ y, int N, int H, int W, int CO,
+                                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                                          int relu, const int* __restrict__ valid_w, double* __restrict__ stats) {
   pdl_prologue();
   constexpr int V = Vec<T>::N;
-  constexpr int G = CO / V;                        // 16-byte pieces per output row
-  constexpr int PITCH = G + 1;                     // odd pitch: conflict-free row writes
-  __shared__ __align__(16) float ws[9 * CO];       // [tap][channel]
-  __shared__ __align__(16) float ss[CO], sb[CO];
-  __shared__ uint4 stage[4][32 * PITCH];
-  for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) ws[(i % 9) * CO + i / 9] = w[i];
-  for (int i = threadIdx.x; i < CO; i += blockDim.x) { ss[i] = scale ? scale[i] : 1.f; sb[i] = shift ? shift[i] : 0.f; }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint4* mine = stage[warp];
-  const long long total = (long long)N * H * W;
-  const long long wstep = (long long)gridDim.x * 4 * 32;
-  for (long long base = ((long long)blockIdx.x * 4 + warp) * 32; base < total; base += wstep) {
-    const long long p = base + lane;
-    const bool live = p < total;
-    float v[9];
-    bool dead = true;
-    if (live) {
-      const int wq = (int)(p % W); const long long q = p / W; const int h = (int)(q % H);
-      dead = valid_w && wq >= valid_w[(int)(q / H)];
+  const int groups = CO / V;
+  const int cg = threadIdx.x % groups, lane_p = threadIdx.x / groups, lanes = blockDim.x / groups;
+  float wr[9][V], sc[V], sh[V];
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+  for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int ih = h + r - 1, iw = wq + s - 1;
-          v[r * 3 + s] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? x[p + (long long)(r - 1) * W + (s - 1)] : 0.f;
-        }
-    } else {
+    for (int j = 0; j < V; ++j) wr[k][j] = w[(cg * V + j) * 9 + k];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) v[k] = 0.f;
+  for (int j = 0; j < V; ++j) { sc[j] = AFFINE ? scale[cg * V + j] : 1.f; sh[j] = AFFINE ? shift[cg * V + j] : 0.f; }
+  float s1[V], s2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  const int runs_w = (W + STEM_RUN - 1) / STEM_RUN;
+  const int items = N * H * runs_w, istep = (int)gridDim.x * lanes;
+  for (int it = blockIdx.x * lanes + lane_p; it < items; it += istep) {
+    const int row = it / runs_w, w0 = (it - row * runs_w) * STEM_RUN;
+    const int n = row / H, h = row - n * H;
+    const int vw = valid_w ? valid_w[n] : W;
+    const float* xr = x + (long long)row * W;
+    float v[3][STEM_RUN + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = h + r - 1;
+      const bool rok = ih >= 0 && ih < H;
+#pragma unroll
+      for (int t = 0; t < STEM_RUN + 2; ++t) {
+        const int iw = w0 + t - 1;
+        v[r][t] = (rok && iw >= 0 && iw < W) ? xr[(r - 1) * W + iw] : 0.f;
+      }
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int c0 = g * V;
+    for (int u = 0; u < STEM_RUN; ++u) {
+      if (w0 + u >= W) break;
       float o[V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) o[j] = 0.f;
+      for (int j = 0; j < V; ++j) {
+        float a = 0.f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int j4 = 0; j4 < V; j4 += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(&ws[k * CO + c0 + j4]);
-          o[j4] = fmaf(v[k], w4.x, o[j4]); o[j4 + 1] = fmaf(v[k], w4.y, o[j4 + 1]);
-          o[j4 + 2] = fmaf(v[k], w4.z, o[j4 + 2]); o[j4 + 3] = fmaf(v[k], w4.w, o[j4 + 3]);
-        }
+          for (int t = 0; t < 3; ++t) a = fmaf(v[r][u + t], wr[r * 3 + t][j], a);
+        if (AFFINE) a = fmaf(a, sc[j], sh[j]);
+        a = relu ? fmaxf(a, 0.f) : a;
+        o[j] = (w0 + u >= vw) ? 0.f : a;
       }
+      Vec<T>::store(y + ((long long)row * W + w0 + u) * CO + cg * V, o);
+      if (STATS) {
 #pragma unroll
-      for (int j4 = 0; j4 < V; j4 += 4) {
-        const float4 a4 = *reinterpret_cast<const float4*>(&ss[c0 + j4]);
-        const float4 b4 = *reinterpret_cast<const float4*>(&sb[c0 + j4]);
-        o[j4] = fmaf(o[j4], a4.x, b4.x); o[j4 + 1] = fmaf(o[j4 + 1], a4.y, b4.y);
-        o[j4 + 2] = fmaf(o[j4 + 2], a4.z, b4.z); o[j4 + 3] = fmaf(o[j4 + 3], a4.w, b4.w);
+        for (int j = 0; j < V; ++j) { const float r_ = round_to<T>(o[j]); s1[j] += r_; s2[j] = fmaf(r_, r_, s2[j]); }
       }
-#pragma unroll
-      for (int j = 0; j < V; ++j) o[j] = dead ? 0.f : (relu ? fmaxf(o[j], 0.f) : o[j]);
-      Vec<T>::store(reinterpret_cast<T*>(&mine[lane * PITCH + g]), o);
     }
-    __syncwarp();
-    // 32 rows x G pieces = one contiguous run in global memory: lane-consecutive 16-byte stores
-    uint4* dst = reinterpret_cast<uint4*>(y + base * CO);
-    const long long npieces = (total - base < 32 ? total - base : 32) * G;
+  }
+  if (STATS) {
+    // lanes of a warp that share a channel group are `groups` apart (groups = 4 or 8 divides 32): butterfly over them first
 #pragma unroll
-    for (int j = 0; j < G; ++j) {
-      const int idx = j * 32 + lane;
-      if (idx < npieces) dst[idx] = mine[(idx / G) * PITCH + (idx % G)];
+    for (int j = 0; j < V; ++j)
+      for (int o = groups; o < 32; o <<= 1) { s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o); }
+    __shared__ float red[2 * 64];
+    for (int i = threadIdx.x; i < 2 * CO; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    if ((threadIdx.x & 31) < groups) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) { atomicAdd(&red[cg * V + j], s1[j]); atomicAdd(&red[CO + cg * V + j], s2[j]); }
     }
-    __syncwarp();
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * CO; i += blockDim.x) atomicAdd(&stats[i], (double)red[i]);
   }
 }
 SVK_API int svk_stem_conv_fwd(const float* x, const float* w, void* y, int N, int H, int W, int Cout, int dtype,
-                              const float* scale, const float* shift, int relu, const int* valid_w, void* stream) {
+                              const float* scale, const float* shift, int relu, const int* valid_w, double* stats,
+                              void* stream) {
   SVK_REQUIRE(x && w && y && N > 0 && H > 0 && W > 0, SVK_E_BADARG, "stem_conv_fwd: bad args");
   SVK_REQUIRE(Cout == 32 || Cout == 64, SVK_E_UNSUPPORTED, "stem_conv_fwd: Cout must be 32 or 64, got %d", Cout);
   SVK_REQUIRE((scale == nullptr) == (shift == nullptr), SVK_E_BADARG, "stem_conv_fwd: scale and shift go together");
-  long long total = (long long)N * H * W;
-  long long b = (total + 127) / 128; long long cap = (long long)svk_num_sms() * 16; if (b > cap) b = cap;
+  SVK_REQUIRE((long long)N * H * W < (1ll << 31), SVK_E_UNSUPPORTED, "stem_conv_fwd: more than 2^31 pixels");
+  const int groups = Cout / (dtype == SVK_BF16 ? 8 : 4);
+  SVK_REQUIRE(groups == 4 || groups == 8 || groups == 16, SVK_E_UNSUPPORTED, "stem_conv_fwd: %d channel groups", groups);
+  const int lanes = 256 / groups;
+  long long items = (long long)N * H * ((W + STEM_RUN - 1) / STEM_RUN);
+  long long b = (items + lanes * 2 - 1) / (lanes * 2); long long cap = (long long)svk_num_sms() * 8; if (b > cap) b = cap; if (b < 1) b = 1;
   cudaStream_t st = as_stream(stream);
   SVK_DISPATCH_DTYPE(dtype, "stem_conv_fwd",
-    if (Cout == 32) svk_launch(stem_fwd_kernel<T, 32>, (int)b, 128, 0, st, x, w, (T*)y, N, H, W, scale, shift, relu, valid_w);
-    else svk_launch(stem_fwd_kernel<T, 64>, (int)b, 128, 0, st, x, w, (T*)y, N, H, W, scale, shift, relu, valid_w);)
+    if (scale && stats) svk_launch(stem_fwd_kernel<T, true, true>, (int)b, 256, 0, st, x, w, (T*)y, N, H, W, Cout, scale, shift, relu, valid_w, stats);
+    else if (scale) svk_launch(stem_fwd_kernel<T, true, false>, (int)b, 256, 0, st, x, w, (T*)y, N, H, W, Cout, scale, shift, relu, valid_w, stats);
+    else if (stats) svk_launch(stem_fwd_kernel<T, false, true>, (int)b, 256, 0, st, x, w, (T*)y, N, H, W, Cout, scale, shift, relu, valid_w, stats);
+    else svk_launch(stem_fwd_kernel<T, false, false>, (int)b, 256, 0, st, x, w, (T*)y, N, H, W, Cout, scale, shift, relu, valid_w, stats);)
   SVK_LAUNCH_CHECK("stem_conv_fwd");
   return 0;
 }
 
-// dw[co][tap] = sum_p dy[p, co] * x[p + shift(tap)].  Thread = (pixel lane, group of V channels): one 16-byte load of
-// dy per pixel, the 9 shifted inputs from L1, 9*V accumulators in registers; warp-shuffle + smem reduction, one fp32
-// atomic per (channel, tap) per block.  HBM-bound on dy (2*Cout bytes per pixel).
+// dw[co][tap] = sum_p dy[p, co] * x[p + shift(tap)].  Same work items as the forward kernel: the 4 dy pieces and the 3 x 6
+// input window of a run are 22 independent loads issued up front (HBM-bound on dy, 2 * Cout bytes per pixel: what matters is
+// bytes in flight — with one 16-byte load in flight per thread the kernel ran at 14 % of the HBM roof), 9 * V accumulators
+// in registers.  Reduction: butterfly over the lanes of a warp that share a channel group, shared-memory atomics per warp,
+// one fp32 atomic per (channel, tap) per block.
 template <typename T>
-__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
-                                                         float* __restrict__ dw, int N, int H, int W, int CO) {
+__global__ void __launch_bounds__(256, 2) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                                            float* __restrict__ dw, int N, int H, int W, int CO) {
   pdl_prologue();
   constexpr int V = Vec<T>::N;
+  typedef typename Vec<T>::raw Raw;
   const int groups = CO / V;                                  // channel groups per pixel (4 or 8 for bf16)
   const int cg = threadIdx.x % groups, lane_p = threadIdx.x / groups, lanes = blockDim.x / groups;
-  long long total = (long long)N * H * W;
   float acc[9][V];
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[k][i] = 0.f;
-  // one pixel per iteration; 32-bit index arithmetic (N*H*W < 2^31 is checked by the launcher): the 64-bit div/mod pair
-  // was a third of the instructions of this issue-bound loop
-  const int tot = (int)total, pstep = (int)(gridDim.x * lanes);
-  for (int p = blockIdx.x * lanes + lane_p; p < tot; p += pstep) {
-    const int wq = p % W, q = p / W, h = q % H;
-    float g[V];
-    Vec<T>::load(dy + (long long)p * CO + cg * V, g);
+  const int runs_w = (W + STEM_RUN - 1) / STEM_RUN;
+  const int items = N * H * runs_w, istep = (int)gridDim.x * lanes;
+  for (int it = blockIdx.x * lanes + lane_p; it < items; it += istep) {
+    const int row = it / runs_w, w0 = (it - row * runs_w) * STEM_RUN;
+    const int h = row % H;
+    Raw raw[STEM_RUN];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int u = 0; u < STEM_RUN; ++u)
+      if (w0 + u < W) raw[u] = *reinterpret_cast<const Raw*>(dy + ((long long)row * W + w0 + u) * CO + cg * V);
+    const float* xr = x + (long long)row * W;
+    float v[3][STEM_RUN + 2];
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ih = h + r - 1, iw = wq + s - 1;
-        const float xv = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? x[p + (r - 1) * W + (s - 1)] : 0.f;
+    for (int r = 0; r < 3; ++r) {
+      const int ih = h + r - 1;
+      const bool rok = ih >= 0 && ih < H;
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[r * 3 + s][i] = fmaf(g[i], xv, acc[r * 3 + s][i]);
+      for (int t = 0; t < STEM_RUN + 2; ++t) {
+        const int iw = w0 + t - 1;
+        v[r][t] = (rok && iw >= 0 && iw < W) ? xr[(r - 1) * W + iw] : 0.f;
       }
+    }
+#pragma unroll
+    for (int u = 0; u < STEM_RUN; ++u) {
+      if (w0 + u >= W) break;
+      float g[V];
+      Vec<T>::unpack(raw[u], g);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[r * 3 + t][i] = fmaf(g[i], v[r][u + t], acc[r * 3 + t][i]);
+    }
   }
-  __shared__ float red[64 * 9];                               // CO <= 64
-  for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
-    for (int i = 0; i < V; ++i) atomicAdd(&red[(cg * V + i) * 9 + k], acc[k][i]);
+    for (int i = 0; i < V; ++i)
+      for (int o = groups; o < 32; o <<= 1) acc[k][i] += __shfl_xor_sync(0xffffffffu, acc[k][i], o);
+  __shared__ float red[64 * 9];                               // CO <= 64
+  for (int i = threadIdx.x; i < CO * 9; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  if ((threadIdx.x & 31) < groups) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int i = 0; i < V; ++i) atomicAdd(&red[(cg * V + i) * 9 + k], acc[k][i]);
+  }
   __syncthreads();
   for (int o = threadIdx.x; o < CO * 9; o += blockDim.x) atomicAdd(&dw[o], red[o]);
 }
@@ -630,9 +665,11 @@ SVK_API int svk_stem_conv_wgrad(const float* x, const void* dy, float* dw, int N
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * Cout * 9, st);
   SVK_REQUIRE(e == cudaSuccess, (int)e, "stem_conv_wgrad: memset failed: %s", cudaGetErrorString(e));
-  long long total = (long long)N * H * W;
-  int lanes = 256 / (Cout / (dtype == SVK_BF16 ? 8 : 4));
-  long long b = (total + lanes * 16 - 1) / (lanes * 16); long long cap = (long long)svk_num_sms() * 2; if (b > cap) b = cap; if (b < 1) b = 1;
+  const int groups = Cout / (dtype == SVK_BF16 ? 8 : 4);
+  SVK_REQUIRE(groups == 4 || groups == 8 || groups == 16, SVK_E_UNSUPPORTED, "stem_conv_wgrad: %d channel groups", groups);
+  const int lanes = 256 / groups;
+  long long items = (long long)N * H * ((W + STEM_RUN - 1) / STEM_RUN);
+  long long b = (items + lanes * 8 - 1) / (lanes * 8); long long cap = (long long)svk_num_sms() * 2; if (b > cap) b = cap; if (b < 1) b = 1;
   SVK_DISPATCH_DTYPE(dtype, "stem_conv_wgrad",
     svk_launch(stem_wgrad_kernel<T>, (int)b, 256, 0, st, x, (const T*)dy, dw, N, H, W, Cout);)
   SVK_LAUNCH_CHECK("stem_conv_wgrad");

@@ -21,6 +21,7 @@ struct Gather3P {
                        //    (descriptors may start at any row: tests/umma_shift_test.cu), accumulator rows i * pitch + j with
                        //    j >= bw discarded.  0: one (bh+2) x bw halo tile per filter column (bw % 8 == 0)
   // staged epilogue (epilogue_v2.cuh): operand tiles of the epilogue arrive by TMA, the output leaves by TMA
+  int n_acc;           // accumulator buffers in TMEM = epilogue warp groups (2: 320 threads, 3: 448 threads)
   int epi2;            // 0: first epilogue (tc_common.cuh)
   int aux_nbuf;        // aux buffers per epilogue group (2 when they fit)
   int aux_slots;       // tile slots per aux buffer: 1 (forward: staging only), 2 (mask, c), 3 (mask, c, shortcut gradient)
@@ -31,7 +32,7 @@ struct Gather3P {
 // Kc == KC (one K chunk per tap: Cin in {32, 64}).  Tap (r = t, s = l) reads halo rows shifted by t (fprop) or 2 - t (dgrad)
 // and the packed filter tap t*3 + l.
 template <int KC, int BN, bool DGRAD>
-__global__ void __launch_bounds__(SVK_GATHER_BOUNDS(BN), 1)
+__global__ void __launch_bounds__(GATHER3_THREADS, 1)
 conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmMask, const __grid_constant__ CUtensorMap tmC,
                        const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOut,
@@ -40,7 +41,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   constexpr int B_BYTES = BN * ROWB;
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
   constexpr uint32_t SBO = 8 * ROWB;
-  constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+  constexpr int TMEM_COLS = 4 * BN;          // room for up to 4 accumulator buffers (q.n_acc of them are used)
   pdl_launch_dependents();
   const GatherP& p = q.g;
   extern __shared__ uint8_t smem_raw[];
@@ -52,9 +53,9 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t wsm = base + a_bytes_all;
   const uint32_t auxoff = a_bytes_all + w_bytes_all;
   const uint32_t aux = base + auxoff;
-  // aux: full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @144, wfull @160, tmem ptr @176
-  const uint32_t bar_full = aux, bar_empty = aux + 64, bar_tfull = aux + 128, bar_tempty = aux + 144, bar_w = aux + 160;
-  const uint32_t bar_afull = aux + 192;                               // staged epilogue: operand tiles of group 0 / 1
+  // aux: full[8] @0, empty[8] @64, wfull @160, tmem ptr @176, afull[8] @192, tfull[4] @256, tempty[4] @288
+  const uint32_t bar_full = aux, bar_empty = aux + 64, bar_tfull = aux + 256, bar_tempty = aux + 288, bar_w = aux + 160;
+  const uint32_t bar_afull = aux + 192;                               // staged epilogue: operand tiles of group g, buffer b at 2 g + b
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + auxoff + 176);
   float* scr = reinterpret_cast<float*>(gbase + auxoff + SMEM_AUX);
   float* coef = reinterpret_cast<float*>(gbase + q.coef_off);
@@ -64,9 +65,9 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t tempty_count = (p.bn_mask && BN >= 128 && blockDim.x == GATHER_THREADS) ? 8u : 4u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < q.n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, tempty_count); }
+    for (int a = 0; a < 4; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, tempty_count); }
     mbar_init(bar_w, 1);
-    for (int a = 0; a < 4; ++a) mbar_init(bar_afull + 8 * a, 1);
+    for (int a = 0; a < 8; ++a) mbar_init(bar_afull + 8 * a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -163,7 +164,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           a_desc += a_stage16;
           if (++stage == q.n_stages) { stage = 0; ph ^= 1u; a_desc = a_desc0; }
           tc_commit(bar_tfull + 8 * acc);
-          if (++acc == 2) { acc = 0; aph ^= 1u; }
+          if (++acc == q.n_acc) { acc = 0; aph ^= 1u; }
           continue;
         }
 #pragma unroll
@@ -183,7 +184,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (++stage == q.n_stages) { stage = 0; ph ^= 1u; a_desc = a_desc0; }
         }
         tc_commit(bar_tfull + 8 * acc);
-        if (++acc == 2) { acc = 0; aph ^= 1u; }
+        if (++acc == q.n_acc) { acc = 0; aph ^= 1u; }
       }
       if (prof && lane == 0) {
         atomicAdd(p.prof + 0, 1ull); atomicAdd(p.prof + 1, (unsigned long long)(clock64() - pt0));
@@ -224,7 +225,8 @@ int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tx,
     configured = true;
   }
   int grid = q.g.total_tiles < svk_num_sms() ? q.g.total_tiles : svk_num_sms();
-  svk_launch(conv_tc_gather3_kernel<KC, BN, DGRAD>, grid, GATHER_THREADS, smem, st, ta, tb, tx[0], tx[1], tx[2], tx[3], q);
+  svk_launch(conv_tc_gather3_kernel<KC, BN, DGRAD>, grid, q.n_acc == 3 ? GATHER3_THREADS : GATHER_THREADS, smem, st, ta, tb, tx[0], tx[1],
+             tx[2], tx[3], q);
   SVK_LAUNCH_CHECK("conv_tc_gather3");
   return 0;
 }
@@ -307,8 +309,18 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   // MMA time (32 channels: ~1,200 cycles) is shorter than its fixed barrier / store latencies, and in the forward pass.
   q.epi2 = (epi2_on && bwd_mode && Nout == 64) ? 1 : 0;
   const size_t w_bytes = (size_t)9 * Kc * Nout * 2;
-  size_t fixed = w_bytes + SMEM_AUX + SCR_BYTES + COEF_BYTES + 1024;
-  size_t limit = 200 * 1024;
+  // Accumulator buffers in TMEM = epilogue warp groups.  Three (448 threads) were tried wherever the first epilogue runs, on
+  // the theory that a narrow tile's epilogue (~2,300 busy cycles) starves the MMA warp of accumulators: same-box A/B
+  // 9.112 / 9.126 ms per step with two vs 9.140 / 9.111 with three, and the 64-channel forward lost an operand stage to the
+  // larger scratch (0.57 -> 0.62 ms).  The issue loop itself runs at ~70 cycles per N = 32 instruction because TMA writes,
+  // UMMA operand reads and the epilogue's transposes share the 128 B/clk of shared memory (profiles/r02_conv_notes.md).
+  // Default two; SVK_GATHER3_GROUPS=3 selects three (parity-tested).
+  static int groups_env = -1;
+  if (groups_env < 0) { const char* e = getenv("SVK_GATHER3_GROUPS"); groups_env = (e && e[0] == '3') ? 3 : 2; }
+  q.n_acc = q.epi2 ? 2 : groups_env;
+  const size_t scr_bytes = q.n_acc == 3 ? SCR3_BYTES : SCR_BYTES;
+  size_t fixed = w_bytes + SMEM_AUX + scr_bytes + COEF_BYTES + 1024;
+  size_t limit = q.n_acc == 3 ? 220 * 1024 : 200 * 1024;
   q.coef_off = 0; q.aux_off = 0;      // filled in below (they depend on the stage count)
   if (q.epi2) {
     q.aux_slots = p.res ? 3 : (p.bn_c ? 2 : 1);
@@ -321,6 +333,9 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
       q.aux_nbuf = 1; fixed = fixed0 + 2 * buf_bytes; limit = G3_SMEM_MAX;
     } else {
       q.epi2 = 0;                     // not enough room next to the resident filter: first epilogue
+      q.n_acc = groups_env;
+      fixed = w_bytes + SMEM_AUX + (q.n_acc == 3 ? SCR3_BYTES : SCR_BYTES) + COEF_BYTES + 1024;
+      limit = q.n_acc == 3 ? 220 * 1024 : 200 * 1024;
     }
   }
   int ns = (int)((limit - fixed) / q.a_stage_bytes);
@@ -330,7 +345,7 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   const size_t smem = fixed + (size_t)ns * q.a_stage_bytes;
   {
     const size_t auxbar = (size_t)ns * q.a_stage_bytes + w_bytes;
-    q.coef_off = (int)(auxbar + SMEM_AUX + (q.epi2 ? 0 : SCR_BYTES));
+    q.coef_off = (int)(auxbar + SMEM_AUX + (q.epi2 ? 0 : (q.n_acc == 3 ? SCR3_BYTES : SCR_BYTES)));
     q.aux_off = (int)((q.coef_off + COEF_BYTES + 1023) / 1024 * 1024);
   }
   CUtensorMap ta, tb, tx[4];

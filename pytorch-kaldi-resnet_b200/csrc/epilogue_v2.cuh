@@ -57,6 +57,7 @@ __device__ __forceinline__ void gather_epilogue_v2(const GatherP& p, const CUten
   constexpr int RG = 128 / NP;                         // row groups of the column pass (8 or 4)
   const int q = warp & 3;
   const int group = (warp - 2) >> 2;
+  const int ngroups = ((int)blockDim.x - 64) >> 7;     // 2 or 3: group g drains accumulator buffer g = every ngroups-th tile
   const int tid_g = ((warp - 2) & 3) * 32 + lane;      // 0..127 inside the group
   const uint32_t bar_id = 1u + (uint32_t)group;
   const uint32_t buf_bytes = (uint32_t)aux_slots * TILE_B;
@@ -95,7 +96,7 @@ __device__ __forceinline__ void gather_epilogue_v2(const GatherP& p, const CUten
     if (has_c) tma_load_4d_1t(dst + TILE_B, tmC, bar, 0, w0, h0, n);
     if (has_res) tma_load_4d_1t(dst + 2 * TILE_B, tmRes, bar, 0, w0, h0, n);
   };
-  const int tile0 = blockIdx.x + group * gridDim.x, tstep = 2 * gridDim.x;
+  const int tile0 = blockIdx.x + group * gridDim.x, tstep = ngroups * gridDim.x;
   if (has_aux && tid_g == 0 && tile0 < p.total_tiles) issue_aux(tile0, 0);
 
   int k = 0;

@@ -181,8 +181,11 @@ constexpr int TC_THREADS = 192;                // wgrad kernels: producer warp, 
 constexpr int GATHER_THREADS = 320;            // fprop/dgrad kernels: producer, MMA, 2 x 4 epilogue warps (one group per
                                                // TMEM accumulator buffer: a tile's epilogue is latency-bound, ~2x the MMA time)
 #define SVK_GATHER_BOUNDS(BN) GATHER_THREADS
+constexpr int GATHER3_THREADS = 448;           // resident-filter kernels (conv_tc3.cu, BN <= 64): producer, MMA, 3 x 4 epilogue warps —
+                                               // three accumulator buffers / epilogue groups: a narrow tile's epilogue takes ~3x its MMA time
 constexpr int SMEM_AUX = 1024;                 // barriers + tmem pointer
 constexpr int SCR_BYTES = 8 * 32 * 36 * 4;     // per-epilogue-warp transpose scratch (33- or 36-word rows)
+constexpr int SCR3_BYTES = 12 * 32 * 36 * 4;   // ... for the 12 epilogue warps of GATHER3_THREADS
 constexpr int COEF_BYTES = 2 * 512 * 4;        // scale/shift staged in smem (Nout <= 512)
 
 // ---- epilogue helpers
@@ -203,8 +206,8 @@ template <int BN>
 __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
                                                 float* scr, const float* coef, int warp, int lane) {
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int ngroups = ((int)blockDim.x - 64) >> 7;   // 1 (192 threads) or 2 (320 threads) epilogue warp groups
-    const int group = (warp - 2) >> 2;      // with 2 groups, group g drains accumulator buffer g = every other tile
+    const int ngroups = ((int)blockDim.x - 64) >> 7;   // 1 (192 threads), 2 (320) or 3 (448) epilogue warp groups
+    const int group = (warp - 2) >> 2;      // with G >= 2 groups, group g drains accumulator buffer g = every G-th tile
     float* myscr = scr + (warp - 2) * 32 * 33;
     constexpr int NCH = BN / 32;
     float s1[NCH], s2[NCH];
@@ -329,7 +332,7 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tempty_arrive(bar_tempty + 8 * acc, p.pair);
-      if (ngroups == 2) aph ^= 1u;
+      if (ngroups >= 2) aph ^= 1u;
       else if (++acc == 2) { acc = 0; aph ^= 1u; }
     }
     if (p.stats && stat_blk >= 0) {
@@ -501,7 +504,7 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tempty_arrive(bar_tempty + 8 * acc, p.pair);
-      if (!SPLIT && ngroups == 2) aph ^= 1u;
+      if (!SPLIT && ngroups >= 2) aph ^= 1u;
       else if (++acc == 2) { acc = 0; aph ^= 1u; }
       cur = nxt;
     }

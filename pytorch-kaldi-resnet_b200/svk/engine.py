@@ -366,8 +366,7 @@ class SpeakerNetEngine(object):
         c0 = self._buf(ws, "c0", (B, F, T, C0))
         a0 = self._buf(ws, "a0", (B, F, T, C0))
         call.svk_stem_conv_fwd(x.data_ptr(), self.stem_conv.weight.data_ptr(), c0.data_ptr(), B, F, T, C0, self.dcode,
-                               0, 0, 0, 0, st)
-        call.svk_channel_stats(c0.data_ptr(), M, C0, self.dcode, self._stats[self.stem_bn.idx].data_ptr(), st)
+                               0, 0, 0, 0, self._stats[self.stem_bn.idx].data_ptr(), st)
         self._bn_train_act(self.stem_bn, c0, a0, M, 1)
         cur, H, W = a0, F, T
         # ---- residual blocks
@@ -850,7 +849,7 @@ class SpeakerNetEngine(object):
         a0 = self._arena("e_a0", (B, F, T, C0))
         sc, sh = self._eval_coefs(self.stem_bn)
         call.svk_stem_conv_fwd(x.data_ptr(), self.stem_conv.weight.data_ptr(), a0.data_ptr(), B, F, T, C0, self.dcode,
-                               sc.data_ptr(), sh.data_ptr(), 1, _ptr(valid[0]) if valid else 0, st)
+                               sc.data_ptr(), sh.data_ptr(), 1, _ptr(valid[0]) if valid else 0, 0, st)
         cur, H, W = a0, F, T
         stage = 0
         for bi, b in enumerate(self.blocks):

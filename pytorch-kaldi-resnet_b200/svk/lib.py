@@ -43,7 +43,7 @@ SIGNATURES = {
     "svk_downsample_dgrad_bn": [_D, _P, _P, _D, _P, _P, _P, ctypes.POINTER(BnBwdFuse), _P],
     "svk_relu_mask_inplace": [_P, _P, _L, _I, _P],
     "svk_conv2d_wgrad": [_D, _P, _P, _P, _P, ctypes.c_size_t, _P],
-    "svk_stem_conv_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P],
+    "svk_stem_conv_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P],
     "svk_stem_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "svk_channel_stats": [_P, _L, _I, _I, _P, _P],
     "svk_bn_finalize": [_P, _L, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P],

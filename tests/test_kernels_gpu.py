@@ -193,8 +193,21 @@ def test_stem_conv():
     xd, wd = x.cuda(), w.cuda()                      # keep the device copies alive across the asynchronous launches
     for code, tol in ((lib.F32, 1e-5), (lib.BF16, 2e-2)):
         y = torch.empty(N, H, W, C, dtype=util.tdtype(code), device="cuda")
-        call.svk_stem_conv_fwd(xd.data_ptr(), wd.data_ptr(), y.data_ptr(), N, H, W, C, code, 0, 0, 0, 0, util.st())
+        stats = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+        call.svk_stem_conv_fwd(xd.data_ptr(), wd.data_ptr(), y.data_ptr(), N, H, W, C, code, 0, 0, 0, 0, stats.data_ptr(), util.st())
         assert util.rel_err(util.nchw(y), ref) <= tol
+        yd = util.nchw(y).double()           # statistics of the values as stored
+        assert util.rel_err(stats.cpu(), torch.cat([yd.sum((0, 2, 3)), (yd * yd).sum((0, 2, 3))])) <= 1e-5
+        # folded scale / shift / ReLU and per-utterance valid widths (extraction path)
+        sc, sh = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+        vw = torch.tensor([51, 7, 30], dtype=torch.int32)
+        scd, shd, vwd = sc.cuda(), sh.cuda(), vw.cuda()
+        call.svk_stem_conv_fwd(xd.data_ptr(), wd.data_ptr(), y.data_ptr(), N, H, W, C, code, scd.data_ptr(), shd.data_ptr(), 1,
+                               vwd.data_ptr(), 0, util.st())
+        ref2 = F.relu(ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+        for n in range(N):
+            ref2[n, :, :, int(vw[n]):] = 0
+        assert util.rel_err(util.nchw(y), ref2) <= tol
         dy = util.bf16_round(torch.randn(N, C, H, W, generator=g))
         dyd = util.nhwc(dy, code)
         dw = torch.empty(C, 9, device="cuda")

@@ -159,3 +159,48 @@ def test_forward_loss_equals_model_plus_criterion(loss_type):
         n0 = launch_count()
         m.engine._head_fwd(m.engine._train_ws[(6, 40, 56)][0]["emb"], y, m.engine._train_ws[(6, 40, 56)][0], None, True)
         assert launch_count() - n0 <= (2 if loss_type == "AAM" else 5), "fused head forward = 2 launches (+ 3 for the BatchNorm1d + ReLU of AAM-v1)"
+
+
+def test_cuda_graph_training_step_equals_eager_steps():
+    """svk.graph.GraphedTrainStep: four replays of the captured step (forward, fused loss, backward with the side-stream
+    weight gradients, SGD) leave the parameters, BatchNorm buffers and losses of four eager steps; a new learning rate
+    captures a new graph."""
+    from model import NeuralSpeakerModel
+    from svk.graph import GraphedTrainStep
+    from svk.optim import SGD
+
+    def run(graphed):
+        torch.manual_seed(9)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = NeuralSpeakerModel(spk_num=101, feat_dim=40, pooling="mean+std", loss="AAM").cuda()
+        opt = SGD(m.parameters(), 0.05, momentum=0.9, weight_decay=1e-4)
+        m.train()
+        g = torch.Generator().manual_seed(10)
+        X = torch.randn(5, 8, 40, 64, generator=g).cuda()
+        Y = torch.randint(0, 101, (5, 8), generator=g).cuda()
+        step = GraphedTrainStep(m, opt, warmup=2) if graphed else None
+        losses = []
+        for i in range(5):
+            if i == 3:
+                opt.param_groups[0]["lr"] = 0.02
+            if graphed:
+                loss, logits = step(X[i], Y[i])
+            else:
+                loss, logits = m.forward_loss(X[i], Y[i])
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+            losses.append(float(loss))
+            assert hasattr(logits, "svk_rank")
+        torch.cuda.synchronize()
+        if graphed:
+            assert len(step._graphs) == 2
+        return losses, {k: v.detach().float().cpu().clone() for k, v in m.state_dict().items()}
+    le, se = run(False)
+    lg, sg = run(True)
+    assert max(abs(a - b) for a, b in zip(le, lg)) <= 2e-3 * max(abs(v) for v in le), (le, lg)
+    for k in se:
+        if k.endswith("num_batches_tracked"):
+            assert int(se[k]) == int(sg[k]) == 5, k
+        else:
+            assert util.rel_err(sg[k], se[k]) <= 5e-3, k       # bf16 path; atomics order differs between runs
