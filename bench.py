@@ -217,12 +217,23 @@ def run_ours(args):
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
     model.train()
 
-    def step(x, y):
+    def eager_step(x, y):
         loss, out = model.forward_loss(x, y)     # = model(x, y) + CrossEntropyLoss, what scripts/train_resnet.py::train calls
         opt.zero_grad()
         loss.backward()
         opt.step()
         return loss
+
+    # --cuda-graph: replay ONE captured CUDA graph per step (svk.graph.GraphedTrainStep: forward, fused loss, backward,
+    # all-reduce, SGD) instead of issuing the ~250 launches from Python.  Measured equal (profiles/r02_launch_overhead.md:
+    # the step is GPU-bound and PDL already hides the launch gaps), so the default stays the eager loop of train_resnet.py.
+    gstep = None
+    if args.cuda_graph:
+        from svk.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(model, opt)
+
+    def step(x, y):
+        return gstep(x, y)[0] if gstep is not None else eager_step(x, y)
 
     def barrier():
         if world > 1:
@@ -246,9 +257,9 @@ def run_ours(args):
         step(x_dev, y_dev)
     # ---- device-resident throughput
     sampler = ClockSampler(local) if rank == 0 else None
-    n0 = lib.launch_count()
+    n0, r0 = lib.launch_count(), (gstep.replays if gstep else 0)
     ms_total = timed(lambda: step(x_dev, y_dev), args.steps)
-    launches = lib.launch_count() - n0
+    launches = lib.launch_count() - n0 + ((gstep.replays - r0) * gstep.launches_per_replay if gstep else 0)
     # ---- end to end through the public API (the loop of scripts/train_resnet.py): every step's batch is copied from
     # pinned host memory (svk.data.DevicePrefetcher: the copy of batch i+1 overlaps step i) and every step's loss is
     # read back to the host (svk.data.ScalarReader: asynchronous copy to a pinned slot, collected two steps later)
@@ -294,6 +305,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "dp%d" % world,
                        "l2": "no flush needed: one step streams ~4 GB of activations per GPU (>> 126 MB L2)",
+                       "launch": "eager (Python issues every launch)" if gstep is None else
+                                 "one CUDA-graph replay per step (%d libsvk kernels per replay)" % gstep.launches_per_replay,
                        "algorithmic_tflops_per_gpu": TRAIN_FLOP_PER_CHUNK * B / (ms_step / 1e3) / 1e12},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
                     "d2h_bytes_per_step": 4},
@@ -308,7 +321,7 @@ def run_ours(args):
     net.engine.wgrad_side = False
     if rank == 0:
         lib.profile_begin()
-    step(x_dev, y_dev)
+    eager_step(x_dev, y_dev)
     prof = lib.profile_end() if rank == 0 else None
     net.engine.wgrad_side = side
     barrier()
@@ -646,6 +659,7 @@ def main():
     ap.add_argument("--cfg5-embeddings", type=int, default=100000)
     ap.add_argument("--cfg5-trials", type=int, default=1000000)
     ap.add_argument("--cfg5-fp32", action="store_true", help="cfg5: exact fp32 cohort products (CUDA cores) instead of tf32 tensor cores")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay one captured CUDA graph per step instead of issuing every launch from Python")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary extraction / scoring numbers")
     ap.add_argument("--profile-out", default="", help="write the per-(kernel, shape) CUDA-event times of one step here")

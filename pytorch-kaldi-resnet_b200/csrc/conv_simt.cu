@@ -555,15 +555,21 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < V; ++j)
       for (int o = groups; o < 32; o <<= 1) { s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o); }
-    __shared__ float red[2 * 64];
-    for (int i = threadIdx.x; i < 2 * CO; i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
+    // fixed-order block reduction (no fp32 atomics: BatchNorm statistics that differ in the last bit between two runs flip
+    // ReLU ties downstream and make a small-batch step irreproducible), then one fp64 atomic per channel per block
+    __shared__ float red[8][2 * 64];
+    const int warp = threadIdx.x >> 5;
     if ((threadIdx.x & 31) < groups) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) { atomicAdd(&red[cg * V + j], s1[j]); atomicAdd(&red[CO + cg * V + j], s2[j]); }
+      for (int j = 0; j < V; ++j) { red[warp][cg * V + j] = s1[j]; red[warp][CO + cg * V + j] = s2[j]; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * CO; i += blockDim.x) atomicAdd(&stats[i], (double)red[i]);
+    for (int i = threadIdx.x; i < 2 * CO; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w_ = 0; w_ < 8; ++w_) t += red[w_][i];
+      atomicAdd(&stats[i], (double)t);
+    }
   }
 }
 SVK_API int svk_stem_conv_fwd(const float* x, const float* w, void* y, int N, int H, int W, int Cout, int dtype,

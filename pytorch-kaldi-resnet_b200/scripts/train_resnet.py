@@ -74,6 +74,7 @@ _FLAGS = (
     (("--multiprocessing-distributed",), dict(action="store_true")),
     # beyond the reference: numerics mode of the kernels
     (("--precision",), dict(default="bf16", choices=["bf16", "fp32"], help="activation storage (fp32 = validation mode)")),
+    (("--cuda-graph",), dict(action="store_true", help="replay one captured CUDA graph per full-size training step")),
 )
 parser = argparse.ArgumentParser(description="B200-native ResNet speaker-embedding training")
 for _names, _opts in _FLAGS:
@@ -252,15 +253,23 @@ def train(train_loader, model, criterion, optimizer, epoch, args):
     end = time.time()
     # batches arrive on the device one step ahead (svk.data.DevicePrefetcher; train_resnet.py:310-311 copied them on the
     # compute stream)
+    graphed = None
+    if getattr(args, "cuda_graph", False):
+        from svk.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(model, optimizer)
     for i, (audios, target) in enumerate(DevicePrefetcher(train_loader, torch.device('cuda', args.gpu))):
         dt = time.time() - end
-        # model(audios, target) + criterion(output, target) (train_resnet.py:316-317) as one call: AAM heads run the fused
-        # AAM-softmax-cross-entropy kernels and hand back the target ranks accuracy() needs
-        loss, output = model.forward_loss(audios, target)
-        meters.update(loss, target_rank(output, target), audios.size(0))
-        optimizer.zero_grad()
-        loss.backward()
-        optimizer.step()
+        if graphed is not None and audios.size(0) == args.batch_size:
+            loss, output = graphed(audios, target)       # the whole step below as one graph replay
+            meters.update(loss, target_rank(output, target), audios.size(0))
+        else:
+            # model(audios, target) + criterion(output, target) (train_resnet.py:316-317) as one call: AAM heads run the
+            # fused AAM-softmax-cross-entropy kernels and hand back the target ranks accuracy() needs
+            loss, output = model.forward_loss(audios, target)
+            meters.update(loss, target_rank(output, target), audios.size(0))
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
         bt = time.time() - end
         end = time.time()
         bt_sum += bt

@@ -26,6 +26,8 @@ class GraphedTrainStep(object):
         self.warmup, self.max_graphs = warmup, max_graphs
         self._graphs = {}
         self._pool = None
+        self.launches_per_replay = 0
+        self.replays = 0
 
     def _key(self, x, y):
         g = self.opt.param_groups[0]
@@ -59,9 +61,12 @@ class GraphedTrainStep(object):
                 self._eager(sx, sy)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        from . import lib
         g = torch.cuda.CUDAGraph()
+        n0 = lib.launch_count()
         with torch.cuda.graph(g, pool=self._pool):
             loss, logits = self._eager(sx, sy)
+        self.launches_per_replay = lib.launch_count() - n0      # libsvk kernels inside one replay (the host counter does not see replays)
         if self._pool is None:
             self._pool = g.pool()
         with torch.no_grad():
@@ -87,6 +92,7 @@ class GraphedTrainStep(object):
         e["x"].copy_(x, non_blocking=True)
         e["y"].copy_(y, non_blocking=True)
         e["graph"].replay()
+        self.replays += 1
         logits = e["logits"]
         if e["rank"] is not None:
             logits.svk_rank = e["rank"]

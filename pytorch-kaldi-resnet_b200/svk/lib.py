@@ -137,6 +137,8 @@ class _Caller(object):
                 rc = fn(*args)
                 if rc != 0:
                     check(rc, name)
+                if TRACE is not None:
+                    TRACE(name)
                 return
             import torch
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -158,6 +160,7 @@ class _Caller(object):
 
 
 PROFILE = None
+TRACE = None           # debugging hook: called with the entry-point name after every libsvk call (tests/diag_graph.py)
 call = _Caller()
 
 

@@ -22,7 +22,7 @@ The network-level op keeps the engine (a Python object owning workspaces and str
 by an integer handle, and the activations a forward saves for its backward by an integer token returned as a tensor.
 """
 import weakref
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -63,11 +63,14 @@ def _engine(handle):
 
 # ------------------------------------------------------------------------------------------------ whole network
 @custom_op("svk::speaker_net_train", mutates_args=(), device_types="cuda")
-def _speaker_net_train(x: Tensor, y: Optional[Tensor], params: List[Tensor], handle: int, save: bool) -> Tuple[Tensor, Tensor]:
-    """(B, F, T) fp32 [, (B,) int64] -> (logits (B, C) fp32, token).  `params` are the module's parameters (views of the
-    engine's flat buffer; listed so autograd records the node).  Functional in its tensor arguments; the BatchNorm running
-    statistics it updates are engine-owned module state (like the workspaces), not arguments — torch only lets functional
-    operators carry an autograd formula.  save=False (no gradient will be asked for) keeps nothing for a backward."""
+def _speaker_net_train(x: Tensor, y: Optional[Tensor], anchor: Tensor, handle: int, save: bool) -> Tuple[Tensor, Tensor]:
+    """(B, F, T) fp32 [, (B,) int64] -> (logits (B, C) fp32, token).  Functional in its tensor arguments; the parameters
+    (views of the engine's flat buffer) and the BatchNorm running statistics it updates are engine-owned state addressed by
+    `handle`, not arguments — torch only lets functional operators carry an autograd formula.  `anchor` is a 1-element
+    tensor that requires grad, created by the caller on the current stream: it is what makes autograd record the node (the
+    backward writes parameter gradients in place and returns none).  Listing the parameters themselves would route the
+    backward through their AccumulateGrad nodes, whose streams predate a CUDA-graph capture and invalidate it
+    (tests/diag_graph.py).  save=False (no gradient will be asked for) keeps nothing for a backward."""
     eng = _engine(handle)
     logits, sv = eng.forward_train(x, y, save=save)
     tok = eng._next_token = getattr(eng, "_next_token", 0) + 1
@@ -78,7 +81,7 @@ def _speaker_net_train(x: Tensor, y: Optional[Tensor], params: List[Tensor], han
 
 
 @register_fake("svk::speaker_net_train")
-def _(x, y, params, handle, save):
+def _(x, y, anchor, handle, save):
     C = _engine(handle).model.last.weight.shape[0]
     return x.new_empty((x.shape[0], C), dtype=torch.float32), torch.empty((), dtype=torch.int64)
 
@@ -105,10 +108,9 @@ class _PendingGuard(object):
 
 
 def _train_setup(ctx, inputs, output):
-    x, y, params, handle, save = inputs
+    x, y, anchor, handle, save = inputs
     ctx.handle = handle
     ctx.token = int(output[1])
-    ctx.nparams = len(params)
     ctx.guard = _PendingGuard(handle, ctx.token)
 
 
@@ -116,23 +118,27 @@ def _train_backward(ctx, dlogits, dtoken):
     eng = _engine(ctx.handle)
     torch.ops.svk.speaker_net_train_backward(dlogits.contiguous(), eng.flat_grads, ctx.handle, ctx.token)
     # parameter gradients were written in place (p.grad = views of the flat gradient buffer): nothing flows through autograd
-    return None, None, [None] * ctx.nparams, None, None
+    return None, None, None, None, None
 
 
 register_autograd("svk::speaker_net_train", _train_backward, setup_context=_train_setup)
 
 
+def _anchor(x, save):
+    return torch.empty(1, dtype=torch.float32, device=x.device, requires_grad=save)
+
+
 def speaker_net_train(engine, x, y):
     engine.ensure_device()
     save = torch.is_grad_enabled() and any(p.requires_grad for p in engine._params)
-    logits, _ = torch.ops.svk.speaker_net_train(x, y, list(engine._params), engine_handle(engine), save)
+    logits, _ = torch.ops.svk.speaker_net_train(x, y, _anchor(x, save), engine_handle(engine), save)
     return logits
 
 
 # ---- the same network with the cross-entropy INSIDE the head (fused AAM-softmax-CE, csrc/aam_fused.cu): returns the mean loss,
 # the margin logits and the target ranks; its backward starts from d loss (a scalar), so d_logits never exists in memory.
 @custom_op("svk::speaker_net_train_loss", mutates_args=(), device_types="cuda")
-def _speaker_net_train_loss(x: Tensor, y: Tensor, params: List[Tensor], handle: int, save: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+def _speaker_net_train_loss(x: Tensor, y: Tensor, anchor: Tensor, handle: int, save: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """(B, F, T) fp32, (B,) int64 -> (mean cross-entropy (), logits (B, C), rank (B,) int32, token).  AAM heads only."""
     eng = _engine(handle)
     logits, sv = eng.forward_train(x, y, save=save)
@@ -147,7 +153,7 @@ def _speaker_net_train_loss(x: Tensor, y: Tensor, params: List[Tensor], handle: 
 
 
 @register_fake("svk::speaker_net_train_loss")
-def _(x, y, params, handle, save):
+def _(x, y, anchor, handle, save):
     C = _engine(handle).model.last.weight.shape[0]
     B = x.shape[0]
     return (x.new_empty((), dtype=torch.float32), x.new_empty((B, C), dtype=torch.float32),
@@ -162,10 +168,9 @@ def _speaker_net_train_loss_backward(dloss: Tensor, flat_grads: Tensor, handle: 
 
 
 def _train_loss_setup(ctx, inputs, output):
-    x, y, params, handle, save = inputs
+    x, y, anchor, handle, save = inputs
     ctx.handle = handle
     ctx.token = int(output[3])
-    ctx.nparams = len(params)
     ctx.guard = _PendingGuard(handle, ctx.token)
     ctx.set_materialize_grads(False)
 
@@ -177,7 +182,7 @@ def _train_loss_backward(ctx, dloss, dlogits, drank, dtoken):
     if dloss is not None:
         eng = _engine(ctx.handle)
         torch.ops.svk.speaker_net_train_loss_backward(dloss, eng.flat_grads, ctx.handle, ctx.token)
-    return None, None, [None] * ctx.nparams, None, None
+    return None, None, None, None, None
 
 
 register_autograd("svk::speaker_net_train_loss", _train_loss_backward, setup_context=_train_loss_setup)
@@ -187,7 +192,7 @@ def speaker_net_train_loss(engine, x, y):
     """-> (loss, logits, rank); loss carries the autograd node."""
     engine.ensure_device()
     save = torch.is_grad_enabled() and any(p.requires_grad for p in engine._params)
-    loss, logits, rank, _ = torch.ops.svk.speaker_net_train_loss(x, y, list(engine._params), engine_handle(engine), save)
+    loss, logits, rank, _ = torch.ops.svk.speaker_net_train_loss(x, y, _anchor(x, save), engine_handle(engine), save)
     return loss, logits, rank
 
 
