@@ -515,6 +515,24 @@ def test_backend_scripts_end_to_end_on_reference_files():
         assert [l.split()[0] for l in got_lines] == [l.split()[0] for l in ref_lines]          # same speakers, same order
         got = np.array([[float(t) for t in l.split()[2:-1]] for l in got_lines])
         assert np.abs(got - fx["spk_mean"]).max() <= 1e-6
+        # compute_mean_byspk.py: the same means from a spk2utt listing (the reference's own script gives the compute_speaker_mean
+        # values within 4e-7 on this fixture: torch.mean of the float32 rows vs a float32 running sum)
+        groups, order = {}, []
+        for line in str(fx["file/utt2spk"]).splitlines():
+            u, sp = line.split()
+            if sp not in groups:
+                groups[sp] = []
+                order.append(sp)
+            groups[sp].append(u)
+        with open(os.path.join(d, "spk2utt"), "w") as f:
+            f.writelines("%s %s\n" % (sp, " ".join(groups[sp])) for sp in reversed(order))
+        r = run(os.path.join(scripts, "compute_mean_byspk.py"), "spk2utt", "emb.iv", "byspk.iv")
+        assert "speakers: %d, feat-dim: %d" % (len(order), fx["spk_mean"].shape[1]) in r.stdout
+        by_lines = open(os.path.join(d, "byspk.iv")).read().splitlines()
+        assert [l.split()[0] for l in by_lines] == list(reversed(order))                        # spk2utt order
+        ref_of = {l.split()[0]: row for l, row in zip(ref_lines, fx["spk_mean"])}
+        for l in by_lines:
+            assert np.abs(np.array([float(t) for t in l.split()[2:-1]]) - ref_of[l.split()[0]]).max() <= 1e-6
         run(os.path.join(scripts, "compute_mean.py"), "emb.iv", "mean.vec")
         txt = open(os.path.join(d, "mean.vec")).read()
         assert txt.startswith(" [ ") and txt.endswith(" ]\n")
