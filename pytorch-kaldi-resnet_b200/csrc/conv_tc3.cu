@@ -264,7 +264,9 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   // measured inside the training step (per step, 13 launches each): 64 channels — fprop 0.626 -> 0.568 ms, fused dgrad
   // 0.767 -> 0.719 ms; 32 channels — fprop unchanged, fused dgrad 0.908 -> 1.328 ms (its per-thread epilogue accesses do
   // not like the narrower tiles), so the 32-channel stage keeps one halo tile per filter column.
-  q.single = (single_on && Nout == 64) ? 1 : 0;
+  static int single_fwd32 = -1;      // A/B: single halo tile also for the 32-channel FORWARD convolution
+  if (single_fwd32 < 0) { const char* e = getenv("SVK_SINGLE_HALO_FWD32"); single_fwd32 = (e && e[0] == '1') ? 1 : 0; }
+  q.single = (single_on && (Nout == 64 || (single_fwd32 && Nout == 32 && !dgrad))) ? 1 : 0;
   p.pitch = 0;
   if (q.single) {
     // single-halo tiles: accumulator rows i * (bw + 2) + j; fewest tiles, then the smallest halo tile (bytes loaded per tile)
