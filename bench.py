@@ -47,17 +47,19 @@ def peaks():
 
 def ncu_traffic():
     """DRAM bytes per launch of the fprop/dgrad kernels from the committed ncu capture of this same command
-    (profiles/summarize_ncu.py over `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`): a static figure measured
-    under the profiler, reported beside the live timings; null when the capture is absent."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01b_ncu_conv_traffic.json")
+    (profiles/r02_collect.sh -> profiles/summarize_ncu_step.py over `ncu --metrics ...dram__bytes_read.sum,
+    dram__bytes_write.sum`, one training step): a static figure measured under the profiler, reported beside the live
+    timings; null when the capture is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_step_metrics.json")
     try:
         with open(path) as f:
-            g = json.load(f)["groups"]
-        ks = [g[k] for k in ("conv_tc_gather_kernel", "conv_tc_gather2_kernel", "conv_tc_gather3_kernel") if k in g]
+            ks = [k for k in json.load(f)["kernels"] if k["kernel"].startswith("conv_tc_gather")]
         n = sum(k["launches"] for k in ks)
-        by = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks)
+        by = sum(k["dram_MB_per_launch"] * 1e6 * k["launches"] for k in ks)
+        pipe = sum(k["tensor_pct_of_elapsed"] * k["time_us"] for k in ks) / sum(k["time_us"] for k in ks)
         return {"traffic": by / n, "traffic_unit": "DRAM bytes per launch (ncu, %d launches of one step)" % n,
-                "traffic_source": "profiles/r01b_ncu_conv_traffic.json"}
+                "traffic_source": "profiles/r02_ncu_step_metrics.json",
+                "ncu_tensor_pipe_pct_of_elapsed": pipe}
     except (OSError, KeyError, ValueError, ZeroDivisionError):
         return {}
 
