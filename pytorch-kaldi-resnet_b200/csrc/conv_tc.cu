@@ -84,6 +84,7 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // uniform registers); the issuing wrappers elect one lane
       int stage = 0; uint32_t ph = 0;
       const uint32_t a_bytes = (uint32_t)(p.bh * p.bw) * Cfg::ROWB;
+      const uint32_t b_bytes = p.sub_n ? (uint32_t)p.sub_n * Cfg::ROWB : (uint32_t)Cfg::B_BYTES;   // column-pair mode: one sub-accumulator's filter rows
       const bool prof = p.prof != nullptr;
       long long pw = 0; const long long pt0 = prof ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -97,7 +98,7 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait_t(bar_empty + 8 * stage, ph ^ 1u, prof, pw);
             const uint32_t sa = stage0 + stage * Cfg::STAGE;
-            mbar_expect_tx(bar_full + 8 * stage, a_bytes + (uint32_t)Cfg::B_BYTES);
+            mbar_expect_tx(bar_full + 8 * stage, a_bytes + b_bytes);
             tma_load_4d(sa, &tmA, bar_full + 8 * stage, kc * KC, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n);
             tma_load_2d(sa + Cfg::A_BYTES, &tmB, bar_full + 8 * stage, kc * KC, p.tap_w[t] * p.Nout + nblk * BN);
             if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; }
@@ -112,7 +113,8 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // uniform registers); the issuing wrappers elect one lane
       // descriptors are base + (byte offset >> 4): nothing is rebuilt inside the loop (the issuing thread is
       // instruction-latency bound, profiles/r01_conv_stage1.md)
-      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      constexpr uint32_t idesc_full = make_idesc(128, BN, 0, 0);
+      const uint32_t idesc = p.sub_n ? make_idesc(128, p.sub_n, 0, 0) : idesc_full;     // column-pair mode: N = one sub-accumulator
       int stage = 0; uint32_t ph = 0;
       int acc = 0; uint32_t aph = 0;
       const uint64_t a_desc0 = make_desc(stage0, 16, Cfg::SBO, Cfg::LAYOUT);
@@ -124,17 +126,22 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait_t(bar_tempty + 8 * acc, aph ^ 1u, prof, pwt);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tile = tmem_base + (uint32_t)(acc * BN);
+        int t = 0, kc = 0;
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait_t(bar_full + 8 * stage, ph, prof, pwf);
           tc_fence_after();
           const uint64_t b_desc = a_desc + (uint64_t)(Cfg::A_BYTES >> 4);
-          tc_mma(d_tmem, a_desc, b_desc, idesc, ks != 0 ? 1u : 0u);
+          // plain: one accumulator, the first k-step overwrites; column-pair: tap t feeds sub-accumulator tap_sub[t]
+          const uint32_t d_tmem = p.sub_n ? d_tile + (uint32_t)(p.tap_sub[t] * p.sub_n) : d_tile;
+          const uint32_t first = p.sub_n ? (uint32_t)(p.tap_first[t] && kc == 0) : (uint32_t)(ks == 0);
+          tc_mma(d_tmem, a_desc, b_desc, idesc, first ? 0u : 1u);
 #pragma unroll
           for (int k = 1; k < KC / 16; ++k) tc_mma(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
           tc_commit(bar_empty + 8 * stage);
           a_desc += (uint64_t)(Cfg::STAGE >> 4);
           if (++stage == Cfg::STAGES) { stage = 0; ph ^= 1u; a_desc = a_desc0; }
+          if (++kc == p.kchunks) { kc = 0; ++t; }
         }
         tc_commit(bar_tfull + 8 * acc);
         if (++acc == 2) { acc = 0; aph ^= 1u; }
@@ -603,22 +610,26 @@ int run_gather(const bf16* in, int N, int Hin, int Win, int Kc,           // gat
   SVK_REQUIRE(Kc % 32 == 0 && Nout % 32 == 0 && Nout <= 512, SVK_E_UNSUPPORTED,
               "conv_tc: channels must be multiples of 32 (<= 512 out), got Kc=%d Nout=%d", Kc, Nout);
   const int KC = (Kc % 64 == 0) ? 64 : 32;
-  int BN = Nout;
+  int BN = p.sub_n ? 2 * Nout : Nout;          // column-pair mode: two sub-accumulators of Nout columns side by side
   if (BN > 256) BN = 256;
   SVK_REQUIRE(BN == 32 || BN == 64 || BN == 128 || BN == 256, SVK_E_UNSUPPORTED, "conv_tc: Nout=%d unsupported", Nout);
-  SVK_REQUIRE(Nout % BN == 0, SVK_E_UNSUPPORTED, "conv_tc: Nout=%d not a multiple of %d", Nout, BN);
+  SVK_REQUIRE(p.sub_n ? (BN == 2 * Nout) : (Nout % BN == 0), SVK_E_UNSUPPORTED, "conv_tc: Nout=%d not a multiple of %d", Nout, BN);
   pick_tile(p.Hc, p.Wc, 128, 128 / (es > 1 ? 1 : 1), 1, &p.bh, &p.bw);
   if (p.bw * es > 256) p.bw = 256 / es;
   p.tiles_h = (p.Hc + p.bh - 1) / p.bh;
   p.tiles_w = (p.Wc + p.bw - 1) / p.bw;
   p.num_pix_tiles = N * p.tiles_h * p.tiles_w;
-  p.n_blocks = Nout / BN;
+  p.n_blocks = p.sub_n ? 1 : Nout / BN;
   p.total_tiles = p.num_pix_tiles * p.n_blocks;
   p.kchunks = Kc / KC;
   p.Nout = Nout;
   p.prof = svk_prof_buffer();
   CUtensorMap ta, tb;
   if (int e = make_nhwc_map(&ta, in, N, Hin, Win, Kc, KC, p.bw, p.bh, es)) return e;
+  if (p.sub_n) {
+    if (int e = make_w_map(&tb, w, (long long)ntaps_total * Nout, Kc, KC, Nout)) return e;       // one sub-accumulator's rows per tap
+    return launch_gather(KC, BN, ta, tb, p, st);
+  }
   if (gather2_applicable(KC, BN, p)) {
     p.pair = 1;
     if (int e = make_w_map(&tb, w, (long long)ntaps_total * Nout, Kc, KC, BN / 2)) return e;     // each CTA loads half a filter block
@@ -682,10 +693,44 @@ int svk_conv2d_fwd_tc(const svk_conv_desc* d, const void* x, const void* w, void
 
 // Stride-2 data gradient: one launch per output parity class; res00 is the additive tensor of class (0,0), res_rest
 // of the other three.
+static bool s2_pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SVK_DISABLE_S2_PAIR"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
 static int dgrad_s2_classes(const svk_conv_desc* d, const void* dy, const void* w, void* dx, const void* res00,
                             const void* res_rest, const void* res_m, const void* mask, const svk_bn_bwd_fuse* bn,
                             cudaStream_t st) {
   const int pad = d->R / 2;
+  if (s2_pair_enabled() && bn && d->R == 3 && !res_m && res_rest == nullptr && (d->Cin == 32 || d->Cin == 64 || d->Cin == 128)) {
+    // Column-pair mode (GatherP::sub_n): one launch per output ROW parity; the two column classes of a tile share the launch,
+    // the dy loads of their common taps excepted, and every epilogue access is a full 2 * Cin-channel run.
+    for (int ph = 0; ph < 2; ++ph) {
+      GatherP p{};
+      p.Hc = (d->H - ph + 1) / 2; p.Wc = (d->W + 1) / 2;
+      if (p.Hc <= 0 || p.Wc <= 0) continue;
+      p.in_mul = 1; p.ntaps = 0; p.sub_n = d->Cin; p.res_sub0 = 1;
+      for (int pw = 0; pw < 2; ++pw) {
+        bool first = true;
+        for (int r = 0; r < d->R; ++r) {
+          if (((ph + pad - r) & 1) != 0) continue;
+          for (int s = 0; s < d->R; ++s) {
+            if (((pw + pad - s) & 1) != 0) continue;
+            int t = p.ntaps++;
+            p.tap_dh[t] = (ph + pad - r) / 2; p.tap_dw[t] = (pw + pad - s) / 2; p.tap_w[t] = r * d->R + s;
+            p.tap_sub[t] = pw; p.tap_first[t] = first ? 1 : 0;
+            first = false;
+          }
+        }
+      }
+      p.Hout = d->H; p.Wout = d->W; p.o_mul = 2; p.o_off_h = ph; p.o_off_w = 0;
+      p.out = (bf16*)dx; p.res = (const bf16*)(ph ? nullptr : res00);
+      p.bn_mask = (const bf16*)bn->mask;
+      if (bn->c) { p.bn_c = (const bf16*)bn->c; p.bn_mean = bn->mean; p.bn_rstd = bn->rstd; p.stats = bn->sums; }
+      if (int e = run_gather((const bf16*)dy, d->N, d->Ho, d->Wo, d->Cout, (const bf16*)w, d->R * d->R, d->Cin, p, 1, st)) return e;
+    }
+    return 0;
+  }
   for (int ph = 0; ph < 2; ++ph) {
     for (int pw = 0; pw < 2; ++pw) {
       GatherP p{};

@@ -30,6 +30,14 @@ struct GatherP {
   int pitch;                  // accumulator row m = i * pitch + j (0: pitch = bw).  pitch = bw + 2: rows with j >= bw are the
                               // pad columns of a single-halo tile (conv_tc3.cu) and are discarded
   int pair;                   // 1: CTA-pair kernel (cta_group::2): accumulator-free barriers live in the pair's leader CTA
+  // Column-pair mode of the stride-2 fused data gradient (sub_n > 0): one launch per output ROW parity computes the two
+  // column parity classes of a tile into two sub-accumulators of sub_n = Nout columns each, laid side by side in TMEM, so an
+  // accumulator row of 2 * Nout values IS the two adjacent output pixels (2 j, 2 j + 1): 2 * Nout contiguous channels in
+  // memory.  The epilogue then reads / writes full lines (the one-class-per-launch form touched 64 B of every 128 B line).
+  int sub_n;                  // 0 = off; else Nout (the tile template's BN is 2 * Nout)
+  int tap_sub[9];             // sub-accumulator of tap t (0: even output column, 1: odd)
+  int tap_first[9];           // 1: first tap of its sub-accumulator (overwrites instead of accumulating)
+  int res_sub0;               // 1: the additive tensor `res` applies to sub-accumulator 0 only (the 1x1 shortcut's even pixels)
 };
 // prof[0] CTAs | MMA warp: [1] loop cycles [2] waiting for operands [3] waiting for a free accumulator |
 // producer: [4] loop cycles [5] waiting for a free stage | first epilogue warp: [6] loop cycles [7] waiting for an accumulator
@@ -198,7 +206,7 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& r, float (&v)[8]) {
 // (the mask of res_m, else bn_mask), c = bn_c.  They are fetched one or two chunks AHEAD of their use so that the global
 // load latency overlaps the MMAs / the previous chunk instead of stalling the 4 epilogue warps once per chunk.
 struct EpiAux { uint4 a[4], b[4], c[4]; };
-struct EpiTile { long long off; int nblk; bool valid, zero_out; };
+struct EpiTile { long long off; int nblk; bool valid, zero_out, valid1; };     // valid1: column-pair mode, the odd pixel exists
 
 // Epilogue of the gather kernels (4 warps): TMEM -> registers -> scale/shift -> +residual -> ReLU -> bf16 -> global, plus the
 // per-channel sum / sum-of-squares of the stored values (BatchNorm batch statistics) reduced through smem.
@@ -392,12 +400,15 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
       const int oh = hc * p.o_mul + p.o_off_h, ow = wc * p.o_mul + p.o_off_w;
       t.off = t.valid ? ((((long long)n * p.Hout + oh) * p.Wout + ow) * p.Nout + t.nblk * BN) : 0;
       t.zero_out = false;
+      t.valid1 = t.valid && (ow + 1 < p.Wout);
       return t;
     };
+    const int sub_chunks = p.sub_n ? (p.sub_n >> 5) : (1 << 30);    // chunks >= sub_chunks belong to the odd output pixel
+    auto chunk_ok = [&](const EpiTile& t, int c) { return (c_first + c) < sub_chunks ? t.valid : t.valid1; };
     auto issue = [&](EpiAux& A, const EpiTile& t, int c) {
-      if (!t.valid) return;
+      if (!chunk_ok(t, c)) return;
       const long long o = t.off + (c_first + c) * 32;
-      if (pa) {
+      if (pa && !(p.res_sub0 && (c_first + c) >= sub_chunks)) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) A.a[g] = *reinterpret_cast<const uint4*>(pa + o + g * 8);
       }
@@ -421,20 +432,22 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
         if (stat_blk >= 0) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
-            atomicAdd(&p.stats[stat_blk * BN + (c_first + c) * 32 + lane], (double)s1[c]);
-            atomicAdd(&p.stats[p.Nout + stat_blk * BN + (c_first + c) * 32 + lane], (double)s2[c]);
+            const int sch = p.sub_n ? (((c_first + c) * 32) & (p.sub_n - 1)) + lane : stat_blk * BN + (c_first + c) * 32 + lane;
+            atomicAdd(&p.stats[sch], (double)s1[c]);
+            atomicAdd(&p.stats[p.Nout + sch], (double)s2[c]);
             s1[c] = 0.f; s2[c] = 0.f;
           }
         }
         stat_blk = cur.nblk;
       }
-      const bool valid = cur.valid;
       mbar_wait_t(bar_tfull + 8 * acc, aph, prof, pw);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         EpiAux& A = aux[c % DEPTH];
+        const bool valid = chunk_ok(cur, c);
+        const bool has_res = pa && !(p.res_sub0 && (c_first + c) >= sub_chunks);
         uint32_t r[32];
         tc_ld32(taddr + (c_first + c) * 32, r);
         uint32_t packed[16];                 // the 32 output values of this row, bf16x2, as stored
@@ -443,7 +456,7 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
           float v8[8], k8[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v8[e] = __uint_as_float(r[g * 8 + e]);
-          if (pa) {
+          if (has_res) {
             float t8[8];
             bf16x8_to_f32(A.a[g], t8);
 #pragma unroll
@@ -487,7 +500,7 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
         else if (has_next) issue(A, nxt, c + DEPTH - NCH);
         if (pc) {
           __syncwarp();
-          const int ch = cur.nblk * BN + (c_first + c) * 32 + lane;
+          const int ch = p.sub_n ? (((c_first + c) * 32) & (p.sub_n - 1)) + lane : cur.nblk * BN + (c_first + c) * 32 + lane;
           const float mu = coef[ch];
           float a1 = 0.f, a2 = 0.f;
 #pragma unroll
@@ -511,8 +524,9 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
     if (pc && stat_blk >= 0) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        atomicAdd(&p.stats[stat_blk * BN + (c_first + c) * 32 + lane], (double)s1[c]);
-        atomicAdd(&p.stats[p.Nout + stat_blk * BN + (c_first + c) * 32 + lane], (double)s2[c]);
+        const int sch = p.sub_n ? (((c_first + c) * 32) & (p.sub_n - 1)) + lane : stat_blk * BN + (c_first + c) * 32 + lane;
+        atomicAdd(&p.stats[sch], (double)s1[c]);
+        atomicAdd(&p.stats[p.Nout + sch], (double)s2[c]);
       }
     }
     if (prof) prof_flush(p.prof, 6, clock64() - pt0, pw, lane);
