@@ -22,6 +22,8 @@ struct Gather3P {
                        //    j >= bw discarded.  0: one (bh+2) x bw halo tile per filter column (bw % 8 == 0)
   // staged epilogue (epilogue_v2.cuh): operand tiles of the epilogue arrive by TMA, the output leaves by TMA
   int n_acc;           // accumulator buffers in TMEM = epilogue warp groups (2: 320 threads, 3: 448 threads)
+  int n_mma;           // MMA-issuing warps: 1, or 2 (one more warp at the end of the CTA; the two alternate tiles)
+  int n_tm;            // accumulator buffers in TMEM (GatherP::n_tm): n_acc, or 2 * n_acc when n_mma == 2 and n_acc is odd
   int epi2;            // 0: first epilogue (tc_common.cuh)
   int aux_nbuf;        // aux buffers per epilogue group (2 when they fit)
   int aux_slots;       // tile slots per aux buffer: 1 (forward: staging only), 2 (mask, c), 3 (mask, c, shortcut gradient)
@@ -32,7 +34,7 @@ struct Gather3P {
 // Kc == KC (one K chunk per tap: Cin in {32, 64}).  Tap (r = t, s = l) reads halo rows shifted by t (fprop) or 2 - t (dgrad)
 // and the packed filter tap t*3 + l.
 template <int KC, int BN, bool DGRAD>
-__global__ void __launch_bounds__(GATHER3_THREADS, 1)
+__global__ void __launch_bounds__(GATHER3_THREADS + 32, 1)
 conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmMask, const __grid_constant__ CUtensorMap tmC,
                        const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOut,
@@ -41,7 +43,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   constexpr int B_BYTES = BN * ROWB;
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
   constexpr uint32_t SBO = 8 * ROWB;
-  constexpr int TMEM_COLS = 4 * BN;          // room for up to 4 accumulator buffers (q.n_acc of them are used)
+  constexpr int TMEM_COLS = 8 * BN;          // room for up to 8 accumulator buffers (q.n_tm of them are used; one CTA per SM)
   pdl_launch_dependents();
   const GatherP& p = q.g;
   extern __shared__ uint8_t smem_raw[];
@@ -53,8 +55,8 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t wsm = base + a_bytes_all;
   const uint32_t auxoff = a_bytes_all + w_bytes_all;
   const uint32_t aux = base + auxoff;
-  // aux: full[8] @0, empty[8] @64, wfull @160, tmem ptr @176, afull[8] @192, tfull[4] @256, tempty[4] @288
-  const uint32_t bar_full = aux, bar_empty = aux + 64, bar_tfull = aux + 256, bar_tempty = aux + 288, bar_w = aux + 160;
+  // aux: wfull @160, tmem ptr @176, afull[8] @192, full[16] @320, empty[16] @448, tfull[8] @576, tempty[8] @640
+  const uint32_t bar_full = aux + 320, bar_empty = aux + 448, bar_tfull = aux + 576, bar_tempty = aux + 640, bar_w = aux + 160;
   const uint32_t bar_afull = aux + 192;                               // staged epilogue: operand tiles of group g, buffer b at 2 g + b
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + auxoff + 176);
   float* scr = reinterpret_cast<float*>(gbase + auxoff + SMEM_AUX);
@@ -65,7 +67,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t tempty_count = (p.bn_mask && BN >= 128 && blockDim.x == GATHER_THREADS) ? 8u : 4u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < q.n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < 4; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, tempty_count); }
+    for (int a = 0; a < 8; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, tempty_count); }
     mbar_init(bar_w, 1);
     for (int a = 0; a < 8; ++a) mbar_init(bar_afull + 8 * a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -111,35 +113,55 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
           mbar_wait_t(bar_empty + 8 * stage, ph ^ 1u, prof, pw);
+#if SVK_DBG_NO_TMA      // diagnostic build: the stage is declared full without loading it
+          if (elect_one()) mbar_arrive(bar_full + 8 * stage);
+#else
           mbar_expect_tx(bar_full + 8 * stage, (uint32_t)q.halo_bytes);
           tma_load_4d(stage0 + stage * q.a_stage_bytes, &tmA, bar_full + 8 * stage, 0, w0 + (DGRAD ? 1 - l : l - 1), h0 - 1, n);
+#endif
           if (++stage == q.n_stages) { stage = 0; ph ^= 1u; }
         }
       }
       if (prof) prof_flush(p.prof, 4, clock64() - pt0, pw, lane);
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || (q.n_mma == 2 && warp == (int)(blockDim.x >> 5) - 1)) {
+    // ===================== MMA issuer(s) =====================
     {   // the WHOLE warp runs this loop (warp-uniform control flow lets ptxas keep descriptors and coordinates in
         // uniform registers); the issuing wrappers elect one lane
       // The issuing thread is instruction-latency bound (profiles/r01: ~180 cycles per UMMA against a 64-cycle tensor
       // floor when descriptors are rebuilt per MMA), so everything is hoisted: a descriptor is base + (byte offset >> 4)
       // in its low 14-bit address field, and all tap offsets are compile-time multiples of loop-invariant registers.
+      // Even so one warp needs ~18 SASS instructions (~80 cycles) per UMMA, twice what an N = 32 instruction occupies the
+      // tensor pipe for (tests/bench_umma.cu: 40 cycles), and no background traffic changes that (profiles/r02_conv_notes.md).
+      // With q.n_mma == 2 a SECOND issuing warp (the CTA's last) takes every other tile of the CTA: its own accumulator
+      // buffer(s), its own positions in the stage ring; tcgen05.commit only tracks the MMAs of the issuing thread.
       constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      const int mma_id = (warp == 1) ? 0 : 1;
+      const int loads_per_tile = q.single ? 1 : 3;
       mbar_wait(bar_w, 0);
       tc_fence_after();
       int stage = 0; uint32_t ph = 0;
       int acc = 0; uint32_t aph = 0;
+      // The stage-ring / accumulator positions move on by one tile that the OTHER issuing warp handles.  Ownership keeps the
+      // parity waits unambiguous: the host makes n_stages a multiple of 2 * loads_per_tile and the number of accumulator
+      // buffers n_tm even, so a stage / an accumulator is only ever used by ONE of the two warps.  (With a buffer shared by
+      // both, a warp that runs ahead — or falls behind — waits for a phase two away from the barrier's, which
+      // try_wait.parity cannot tell from the right one: corrupted tiles and stalled pipelines in tests/stress_conv.py.)
+      auto skip_tile = [&]() {
+        stage += loads_per_tile;
+        while (stage >= q.n_stages) { stage -= q.n_stages; ph ^= 1u; }
+        if (++acc == q.n_tm) { acc = 0; aph ^= 1u; }
+      };
+      if (mma_id) skip_tile();
       const uint64_t row16 = (uint64_t)(((uint32_t)p.bw * ROWB) >> 4);      // one halo image row, in 16-byte units
       const uint64_t a_desc0 = make_desc(stage0, 16, SBO, LAYOUT);
       const uint64_t a_stage16 = (uint64_t)((uint32_t)q.a_stage_bytes >> 4);
       const uint64_t b_desc0 = make_desc(wsm, 16, SBO, LAYOUT);
-      uint64_t a_desc = a_desc0;
-      const bool prof = p.prof != nullptr;
+      const bool prof = p.prof != nullptr && mma_id == 0;
       long long pwf = 0, pwt = 0; const long long pt0 = prof ? clock64() : 0;
       unsigned long long gt0 = 0;
       if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x + mma_id * gridDim.x; tile < p.total_tiles; tile += q.n_mma * gridDim.x) {
         mbar_wait_t(bar_tempty + 8 * acc, aph ^ 1u, prof, pwt);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -147,6 +169,7 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           // one halo tile: tap (r = t, s = l) reads rows shifted by r' * pitch + s' (fprop r' = t, s' = l; dgrad 2 - t, 2 - l)
           mbar_wait_t(bar_full + 8 * stage, ph, prof, pwf);
           tc_fence_after();
+          const uint64_t a_desc = a_desc0 + (uint64_t)(uint32_t)stage * a_stage16;
           const uint64_t pix16 = (uint64_t)(ROWB >> 4);                               // one pixel row, in 16-byte units
           const uint64_t prow16 = (uint64_t)(((uint32_t)p.pitch * ROWB) >> 4);        // one halo image row
 #pragma unroll
@@ -161,30 +184,28 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
           }
           tc_commit(bar_empty + 8 * stage);
-          a_desc += a_stage16;
-          if (++stage == q.n_stages) { stage = 0; ph ^= 1u; a_desc = a_desc0; }
-          tc_commit(bar_tfull + 8 * acc);
-          if (++acc == q.n_acc) { acc = 0; aph ^= 1u; }
-          continue;
-        }
+          if (++stage == q.n_stages) { stage = 0; ph ^= 1u; }
+        } else {
 #pragma unroll
-        for (int l = 0; l < 3; ++l) {
-          mbar_wait_t(bar_full + 8 * stage, ph, prof, pwf);
-          tc_fence_after();
+          for (int l = 0; l < 3; ++l) {
+            mbar_wait_t(bar_full + 8 * stage, ph, prof, pwf);
+            tc_fence_after();
+            const uint64_t a_desc = a_desc0 + (uint64_t)(uint32_t)stage * a_stage16;
 #pragma unroll
-          for (int t = 0; t < 3; ++t) {
-            const uint64_t ad_t = a_desc + (uint64_t)(DGRAD ? 2 - t : t) * row16;
-            const uint64_t bd_t = b_desc0 + (uint64_t)(((t * 3 + l) * B_BYTES) >> 4);
+            for (int t = 0; t < 3; ++t) {
+              const uint64_t ad_t = a_desc + (uint64_t)(DGRAD ? 2 - t : t) * row16;
+              const uint64_t bd_t = b_desc0 + (uint64_t)(((t * 3 + l) * B_BYTES) >> 4);
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k)
-              tc_mma(d_tmem, ad_t + 2 * k, bd_t + 2 * k, idesc, (l | t | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < KC / 16; ++k)
+                tc_mma(d_tmem, ad_t + 2 * k, bd_t + 2 * k, idesc, (l | t | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(bar_empty + 8 * stage);
+            if (++stage == q.n_stages) { stage = 0; ph ^= 1u; }
           }
-          tc_commit(bar_empty + 8 * stage);
-          a_desc += a_stage16;
-          if (++stage == q.n_stages) { stage = 0; ph ^= 1u; a_desc = a_desc0; }
         }
         tc_commit(bar_tfull + 8 * acc);
-        if (++acc == q.n_acc) { acc = 0; aph ^= 1u; }
+        if (++acc == q.n_tm) { acc = 0; aph ^= 1u; }
+        if (q.n_mma == 2) skip_tile();
       }
       if (prof && lane == 0) {
         atomicAdd(p.prof + 0, 1ull); atomicAdd(p.prof + 1, (unsigned long long)(clock64() - pt0));
@@ -225,7 +246,7 @@ int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tx,
     configured = true;
   }
   int grid = q.g.total_tiles < svk_num_sms() ? q.g.total_tiles : svk_num_sms();
-  svk_launch(conv_tc_gather3_kernel<KC, BN, DGRAD>, grid, q.n_acc == 3 ? GATHER3_THREADS : GATHER_THREADS, smem, st, ta, tb, tx[0], tx[1],
+  svk_launch(conv_tc_gather3_kernel<KC, BN, DGRAD>, grid, (q.n_acc == 3 ? GATHER3_THREADS : GATHER_THREADS) + (q.n_mma == 2 ? 32 : 0), smem, st, ta, tb, tx[0], tx[1],
              tx[2], tx[3], q);
   SVK_LAUNCH_CHECK("conv_tc_gather3");
   return 0;
@@ -309,17 +330,30 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   // Measured inside the training step (profiles/r02_epilogue_v2.md): the staged epilogue wins where the first one is bound
   // by L1 wavefronts — the fused data gradient of the 64-channel stage (0.95 -> 0.74 ms per step) — and loses where a tile's
   // MMA time (32 channels: ~1,200 cycles) is shorter than its fixed barrier / store latencies, and in the forward pass.
-  q.epi2 = (epi2_on && bwd_mode && Nout == 64) ? 1 : 0;
+  // SVK_EPI2_MODE (A/B): bit 0 = also the 32-channel fused dgrad, bit 1 = the 64-channel training forward, bit 2 = the
+  // 32-channel training forward
+  static int epi2_mode = -1;
+  if (epi2_mode < 0) { const char* e = getenv("SVK_EPI2_MODE"); epi2_mode = e ? atoi(e) : 0; }
+  const bool fwd_mode = !dgrad && p.stats && !p.bn_mask && !p.res && !p.res_m && !p.scale && !p.valid_w && !p.relu;
+  q.epi2 = (epi2_on && bwd_mode && (Nout == 64 || (epi2_mode & 1))) ? 1 : 0;
+  if (epi2_on && fwd_mode && ((Nout == 64 && (epi2_mode & 2)) || (Nout == 32 && (epi2_mode & 4)))) q.epi2 = 1;
   const size_t w_bytes = (size_t)9 * Kc * Nout * 2;
-  // Accumulator buffers in TMEM = epilogue warp groups.  Three (448 threads) were tried wherever the first epilogue runs, on
-  // the theory that a narrow tile's epilogue (~2,300 busy cycles) starves the MMA warp of accumulators: same-box A/B
-  // 9.112 / 9.126 ms per step with two vs 9.140 / 9.111 with three, and the 64-channel forward lost an operand stage to the
-  // larger scratch (0.57 -> 0.62 ms).  The issue loop itself runs at ~70 cycles per N = 32 instruction because TMA writes,
-  // UMMA operand reads and the epilogue's transposes share the 128 B/clk of shared memory (profiles/r02_conv_notes.md).
-  // Default two; SVK_GATHER3_GROUPS=3 selects three (parity-tested).
-  static int groups_env = -1;
-  if (groups_env < 0) { const char* e = getenv("SVK_GATHER3_GROUPS"); groups_env = (e && e[0] == '3') ? 3 : 2; }
-  q.n_acc = q.epi2 ? 2 : groups_env;
+  // Issuing warps / epilogue groups / operand stages.  One warp issues a UMMA every ~80 cycles (about 18 SASS instructions
+  // each), twice what an N = 32 instruction occupies the tensor pipe for (tests/bench_umma.cu: 40 cycles under any background
+  // shared-memory traffic), so a second issuing warp taking every other tile doubles the issue rate; the loop then waits on
+  // the epilogue (three groups instead of two) and on operands (TMA latency under load is ~2 tiles of MMA time: 12 stages
+  // instead of 6).  Measured inside the training step, per step (profiles/r02_conv_notes.md): forward 32 channels 0.684 ->
+  // 0.594 ms, 64 channels 0.545 -> 0.533 ms; the fused data gradients are bound by their four or five operand streams
+  // (0.90 -> 0.93 ms for 32 channels with the same change, 0.71 -> 0.74 ms for 64), so they keep one warp / two groups / 6.
+  // SVK_GATHER3_MMA / _GROUPS / _STAGES override the choice for every launch (A/B, tests/stress_conv.py).
+  static int groups_env = -1, mma_env = -1, stages_env = -1;
+  if (groups_env < 0) { const char* e = getenv("SVK_GATHER3_GROUPS"); groups_env = (e && (e[0] == '2' || e[0] == '3')) ? e[0] - '0' : 0; }
+  if (mma_env < 0) { const char* e = getenv("SVK_GATHER3_MMA"); mma_env = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
+  if (stages_env < 0) { const char* e = getenv("SVK_GATHER3_STAGES"); stages_env = e ? atoi(e) : 0; if (stages_env > 16) stages_env = 16; }
+  const bool wide = !dgrad;
+  const int groups_sel = groups_env ? groups_env : (wide ? 3 : 2);
+  q.n_acc = q.epi2 ? 2 : groups_sel;
+  q.n_mma = mma_env ? mma_env : (wide ? 2 : 1);
   const size_t scr_bytes = q.n_acc == 3 ? SCR3_BYTES : SCR_BYTES;
   size_t fixed = w_bytes + SMEM_AUX + scr_bytes + COEF_BYTES + 1024;
   size_t limit = q.n_acc == 3 ? 220 * 1024 : 200 * 1024;
@@ -329,21 +363,37 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
     q.aux_box_bytes = p.bh * p.bw * Nout * 2;
     const size_t buf_bytes = (size_t)q.aux_slots * 128 * Nout * 2;
     const size_t fixed0 = w_bytes + SMEM_AUX + COEF_BYTES + 1024 /* align aux */ + 1024 /* align base */;
-    if ((G3_SMEM_MAX - fixed0 - 4 * buf_bytes) / q.a_stage_bytes >= 3 && G3_SMEM_MAX > fixed0 + 4 * buf_bytes) {
-      q.aux_nbuf = 2; fixed = fixed0 + 4 * buf_bytes; limit = G3_SMEM_MAX;
-    } else if ((G3_SMEM_MAX - fixed0 - 2 * buf_bytes) / q.a_stage_bytes >= 2 && G3_SMEM_MAX > fixed0 + 2 * buf_bytes) {
-      q.aux_nbuf = 1; fixed = fixed0 + 2 * buf_bytes; limit = G3_SMEM_MAX;
-    } else {
+    // epilogue groups x aux buffers per group, in order of preference; each needs room for `want` operand stages next to it
+    static int epi2_groups = -1;
+    if (epi2_groups < 0) { const char* e = getenv("SVK_EPI2_GROUPS"); epi2_groups = (e && e[0] == '3') ? 3 : 2; }
+    const int want = q.single ? 3 : 6;
+    bool placed = false;
+    for (int g = epi2_groups; g >= 2 && !placed; --g) {
+      for (int nb = 2; nb >= 1 && !placed; --nb) {
+        const size_t f = fixed0 + (size_t)g * nb * buf_bytes;
+        if (f < (size_t)G3_SMEM_MAX && (int)((G3_SMEM_MAX - f) / q.a_stage_bytes) >= (nb == 2 ? want : (g == 3 ? 3 : 2))) {
+          q.n_acc = g; q.aux_nbuf = nb; fixed = f; limit = G3_SMEM_MAX; placed = true;
+        }
+      }
+    }
+    if (!placed) {
       q.epi2 = 0;                     // not enough room next to the resident filter: first epilogue
-      q.n_acc = groups_env;
+      q.n_acc = groups_sel;
       fixed = w_bytes + SMEM_AUX + (q.n_acc == 3 ? SCR3_BYTES : SCR_BYTES) + COEF_BYTES + 1024;
       limit = q.n_acc == 3 ? 220 * 1024 : 200 * 1024;
     }
   }
   int ns = (int)((limit - fixed) / q.a_stage_bytes);
-  if (ns > 6) ns = 6;
+  const int ns_cap = stages_env >= 2 ? stages_env : (wide ? 12 : 6);
+  if (ns > ns_cap) ns = ns_cap;
+  if (q.n_mma == 2) {                // every stage belongs to one issuing warp (see the kernel's skip_tile)
+    const int unit = 2 * (q.single ? 1 : 3);
+    if (ns >= unit) ns = ns / unit * unit; else q.n_mma = 1;
+  }
   SVK_REQUIRE(ns >= 2, SVK_E_UNSUPPORTED, "conv_tc3: not enough shared memory for 2 stages");
   q.n_stages = ns;
+  q.n_tm = (q.n_mma == 2 && (q.n_acc & 1)) ? 2 * q.n_acc : q.n_acc;
+  q.g.n_tm = q.n_tm;
   const size_t smem = fixed + (size_t)ns * q.a_stage_bytes;
   {
     const size_t auxbar = (size_t)ns * q.a_stage_bytes + w_bytes;

@@ -99,6 +99,8 @@ __device__ __forceinline__ void gather_epilogue_v2(const GatherP& p, const CUten
   const int tile0 = blockIdx.x + group * gridDim.x, tstep = ngroups * gridDim.x;
   if (has_aux && tid_g == 0 && tile0 < p.total_tiles) issue_aux(tile0, 0);
 
+  const int n_tm = p.n_tm ? p.n_tm : ngroups;          // accumulator buffers (GatherP::n_tm): this group's tiles use group, group + ngroups, ...
+  int tbuf = group; uint32_t tph = 0;
   int k = 0;
   for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++k) {
     int pt = tile;
@@ -112,10 +114,10 @@ __device__ __forceinline__ void gather_epilogue_v2(const GatherP& p, const CUten
     const uint8_t* t_c = t_out + TILE_B;
     const uint8_t* t_res = t_out + 2 * TILE_B;
 
-    mbar_wait(bar_tfull + 8 * group, (uint32_t)(k & 1));
+    mbar_wait(bar_tfull + 8 * tbuf, tph);
     tc_fence_after();
     if (has_aux) mbar_wait(bar_afull + 8 * (group * 2 + b), (uint32_t)((nbuf == 2 ? (k >> 1) : k) & 1));
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * BN);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tbuf * BN);
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
@@ -152,7 +154,9 @@ __device__ __forceinline__ void gather_epilogue_v2(const GatherP& p, const CUten
     // the accumulator is drained: hand it back to the MMA warp before the store / statistics
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_tempty + 8 * group);
+    if (lane == 0) mbar_arrive(bar_tempty + 8 * tbuf);
+    tbuf += ngroups;
+    if (tbuf >= n_tm) { tbuf -= n_tm; tph ^= 1u; }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // staged rows -> visible to the TMA store
     if (nbuf == 2 && tid_g == 0) tma_store_wait_read();              // store k-1 has read the OTHER buffer
     named_bar_sync(bar_id, 128);

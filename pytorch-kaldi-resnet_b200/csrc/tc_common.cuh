@@ -38,6 +38,11 @@ struct GatherP {
   int tap_sub[9];             // sub-accumulator of tap t (0: even output column, 1: odd)
   int tap_first[9];           // 1: first tap of its sub-accumulator (overwrites instead of accumulating)
   int res_sub0;               // 1: the additive tensor `res` applies to sub-accumulator 0 only (the 1x1 shortcut's even pixels)
+  // Accumulator buffers in TMEM, used round-robin by the CTA's tiles (tile k of the CTA -> buffer k % n_tm).  0 = one per
+  // epilogue group (two for a single group / a SPLIT epilogue).  conv_tc3.cu with two MMA-issuing warps and three epilogue
+  // groups uses 6, so that every buffer has exactly ONE issuing warp (k % 2) and ONE draining group (k % 3): a barrier whose
+  // waiters can be two phases apart cannot be waited on by parity.
+  int n_tm;
 };
 // prof[0] CTAs | MMA warp: [1] loop cycles [2] waiting for operands [3] waiting for a free accumulator |
 // producer: [4] loop cycles [5] waiting for a free stage | first epilogue warp: [6] loop cycles [7] waiting for an accumulator
@@ -224,6 +229,8 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
     int stat_blk = -1;
     const int chl = 2 * (lane & 15) + (lane >> 4);    // channel (within a chunk) whose sums this lane keeps
     int acc = group; uint32_t aph = 0;
+    const int astep = ngroups >= 2 ? ngroups : 1;                       // this group's next tile is `astep` buffers further on
+    const int n_tm = p.n_tm ? p.n_tm : (ngroups >= 2 ? ngroups : 2);
     const bool prof = p.prof != nullptr && warp == 2;
     long long pw = 0; const long long pt0 = prof ? clock64() : 0;
     const int m = q * 32 + lane;            // accumulator row = pixel index inside the tile (loop invariant)
@@ -260,6 +267,10 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
       for (int c = 0; c < NCH; ++c) {
         uint32_t r[32];
         tc_ld32(taddr + c * 32, r);
+#if SVK_DBG_EPI_SKIP == 1   // diagnostic build: drain the accumulator and do nothing else
+        s1[c] += __uint_as_float(r[0]) + __uint_as_float(r[31]);
+        continue;
+#endif
         float v[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
@@ -302,7 +313,11 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
           __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
           packed[e] = valid ? *reinterpret_cast<uint32_t*>(&h) : 0u;
         }
+#if SVK_DBG_EPI_SKIP == 2   // diagnostic build: no global stores
+        if (valid && packed[3] == 0x12345678u) {
+#else
         if (valid) {
+#endif
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(p.out + off + c * 32 + g * 8) =
@@ -340,8 +355,8 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tempty_arrive(bar_tempty + 8 * acc, p.pair);
-      if (ngroups >= 2) aph ^= 1u;
-      else if (++acc == 2) { acc = 0; aph ^= 1u; }
+      acc += astep;
+      if (acc >= n_tm) { acc -= n_tm; aph ^= 1u; }
     }
     if (p.stats && stat_blk >= 0) {
 #pragma unroll
@@ -381,6 +396,8 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
     for (int c = 0; c < NCH; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
     int stat_blk = -1;
     int acc = SPLIT ? 0 : group; uint32_t aph = 0;
+    const int astep = (!SPLIT && ngroups >= 2) ? ngroups : 1;
+    const int n_tm = (!SPLIT && p.n_tm) ? p.n_tm : ((!SPLIT && ngroups >= 2) ? ngroups : 2);
     const bool prof = p.prof != nullptr && warp == 2;
     long long pw = 0; const long long pt0 = prof ? clock64() : 0;
     const int m = q * 32 + lane;
@@ -517,8 +534,8 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tempty_arrive(bar_tempty + 8 * acc, p.pair);
-      if (!SPLIT && ngroups >= 2) aph ^= 1u;
-      else if (++acc == 2) { acc = 0; aph ^= 1u; }
+      acc += astep;
+      if (acc >= n_tm) { acc -= n_tm; aph ^= 1u; }
       cur = nxt;
     }
     if (pc && stat_blk >= 0) {

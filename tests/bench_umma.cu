@@ -310,6 +310,131 @@ void run_sw64(int grid, int iters) {
   CK(cudaFree(d));
 }
 
+
+// SWIZZLE_64B operands as the stage-1 kernel uses them, with the traffic that shares the shared-memory port in the real
+// kernel: warp 1 streams bulk copies global -> shared (two 8 KB copies in flight, back to back) when bg & 1, warps 2-3 do the
+// epilogue-like row writes / column reads when bg & 2.  A_SHIFT: the A descriptor of UMMA pair s starts (s % 3) * 8 rows into
+// the stage (tap offsets of a halo tile).  Reports cycles per UMMA and the bytes the background copies delivered per cycle.
+template <int N>
+__global__ void __launch_bounds__(128, 1) umma_rate_sw64_bg_kernel(int iters, int bg, int a_shift, int commit_every, int tile_len,
+                                                                    const uint8_t* __restrict__ src, Result* res) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ __align__(8) uint64_t bar_ld[2];
+  __shared__ __align__(8) uint64_t bar_dummy;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ volatile int stop_flag;
+  __shared__ float hammer_buf[2 * 32 * 36];
+  for (int i = threadIdx.x; i < (81920 + 4 * N * 64 + 16384) / 2; i += blockDim.x) reinterpret_cast<__nv_bfloat16*>(gbase)[i] = __float2bfloat16(0.5f);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_done)), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_ld[0])), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_ld[1])), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_dummy)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    stop_flag = 0;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_ptr;
+  bool ok = true;
+  long long c0 = 0, c1 = 0;
+  unsigned long long copied = 0;
+  if (warp == 0) {
+    constexpr uint32_t idesc = make_idesc(128, N);
+    c0 = clock64();
+    uint32_t accum = 0;
+    int cnt = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {          // A: 8 regions of 10 KB (128 + 32 rows x 64 B) ; B at +80 KB, N rows x 64 B each
+        const uint64_t a0 = make_desc(base + s * 10240 + (a_shift ? (s % 3) * 512 : 0), 16, 512, 4);
+        const uint64_t b0 = make_desc(base + 81920 + (s & 3) * (N * 64), 16, 512, 4);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          tc_mma<1>(tmem_base + (tile_len ? (uint32_t)(((cnt / tile_len) & 1) * N) : 0u), a0 + 2 * k, b0 + 2 * k, idesc,
+                    (tile_len && cnt % tile_len == 0) ? 0u : accum);
+          accum = 1; ++cnt;
+        }
+        // commit_every UMMAs: a tcgen05.commit to a barrier nobody waits on (the stage-free / tile-done signals of a pipeline)
+        if (commit_every && cnt % commit_every == 0) tc_commit<1>(smem_u32(&bar_dummy));
+      }
+    }
+    tc_commit<1>(smem_u32(&bar_done));
+    ok = mbar_wait(smem_u32(&bar_done), 0);
+    c1 = clock64();
+    stop_flag = 1;
+  } else if (warp == 1 && (bg & 1)) {
+    // destination: a 16 KB scratch behind the operands (never read by the MMAs)
+    const uint32_t dst = base + 81920 + 4 * (N * 64);
+    const uint8_t* my_src = src + (size_t)blockIdx.x * 65536;
+    uint32_t ph[2] = {0, 0};
+    int n = 0;
+    if (lane == 0) {
+      for (int b = 0; b < 2; ++b) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_ld[b])), "r"(8192) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + b * 8192), "l"(my_src + b * 8192), "r"(8192), "r"(smem_u32(&bar_ld[b])) : "memory");
+      }
+      while (!stop_flag) {
+        const int b = n & 1;
+        mbar_wait(smem_u32(&bar_ld[b]), ph[b]); ph[b] ^= 1;
+        copied += 8192;
+        ++n;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_ld[b])), "r"(8192) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + b * 8192), "l"(my_src + ((n + 1) & 7) * 8192), "r"(8192), "r"(smem_u32(&bar_ld[b])) : "memory");
+      }
+      mbar_wait(smem_u32(&bar_ld[0]), ph[0]);
+      mbar_wait(smem_u32(&bar_ld[1]), ph[1]);
+      res[blockIdx.x].ns = copied;
+    }
+  } else if (warp >= 2 && (bg & 2)) {
+    float* my = hammer_buf + (warp - 2) * 32 * 36;
+    float acc = 0.f;
+    while (!stop_flag) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(my + lane * 36 + g * 4) = make_float4(acc, 1.f, 2.f, 3.f);
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 32; ++r) acc += my[r * 36 + lane];
+      __syncwarp();
+    }
+    if (acc == 12345.678f) res[0].bad = -1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { res[blockIdx.x].cycles = (unsigned long long)(c1 - c0); res[blockIdx.x].timeout = ok ? 0 : 1; }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+}
+template <int N>
+void run_sw64_bg(int grid, int iters, int bg, int a_shift, int commit_every = 0, int tile_len = 0) {
+  const int smem = 81920 + 4 * N * 64 + 16384 + 1024;
+  CK(cudaFuncSetAttribute(umma_rate_sw64_bg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  Result* d; CK(cudaMalloc(&d, sizeof(Result) * grid)); CK(cudaMemset(d, 0, sizeof(Result) * grid));
+  uint8_t* src; CK(cudaMalloc(&src, (size_t)grid * 65536)); CK(cudaMemset(src, 0, (size_t)grid * 65536));
+  for (int rep = 0; rep < 2; ++rep) { CK(cudaMemset(d, 0, sizeof(Result) * grid)); umma_rate_sw64_bg_kernel<N><<<grid, 128, smem>>>(iters, bg, a_shift, commit_every, tile_len, src, d); CK(cudaDeviceSynchronize()); }
+  std::vector<Result> h(grid); CK(cudaMemcpy(h.data(), d, sizeof(Result) * grid, cudaMemcpyDeviceToHost));
+  double cyc = 0, bytes = 0; int to = 0;
+  for (int i = 0; i < grid; ++i) { cyc += h[i].cycles; bytes += h[i].ns; to += h[i].timeout; }
+  cyc /= grid; bytes /= grid;
+  const double n_umma = (double)iters * 16;
+  printf("SW64 M=128 N=%3d bulk-copy=%d hammer=%d tap-shift=%d commit-every=%2d tile=%2d : %7.1f cycles/UMMA  %6.1f MAC/clk/SM  copies %5.1f B/clk  timeout=%d\n", N,
+         bg & 1, (bg >> 1) & 1, a_shift, commit_every, tile_len, cyc / n_umma, n_umma * 128.0 * N * 16.0 / cyc, bytes / cyc, to);
+  fflush(stdout);
+  CK(cudaFree(d)); CK(cudaFree(src));
+}
+
 template <int N, int A_MN, int B_MN>
 void run_mn(int grid, int iters, int b_lbo) {
   const int smem = 98304 + 1024;
@@ -368,6 +493,23 @@ int main(int argc, char** argv) {
   const int grid = sms & ~1;
   const int iters = argc > 1 ? atoi(argv[1]) : 512;
   printf("SMs %d, %d UMMAs per CTA per launch\n", sms, iters * 4 * 4);
+  if (argc > 4) {     // cost of tcgen05.commit / of starting a new accumulator inside the instruction stream
+    for (int ce : {0, 18, 6, 2}) run_sw64_bg<32>(grid, iters, 0, 1, ce, 0);
+    for (int ce : {0, 18, 6}) run_sw64_bg<32>(grid, iters, 0, 1, ce, 18);
+    for (int ce : {0, 6}) run_sw64_bg<64>(grid, iters, 0, 1, ce, 18);
+    for (int ce : {0, 6}) run_sw64_bg<96>(grid, iters, 0, 1, ce, 6);
+    return 0;
+  }
+  if (argc > 3) {     // SWIZZLE_64B operands under shared-memory-port contention (stage-1 conv configuration)
+    for (int bg = 0; bg < 4; ++bg) {
+      run_sw64_bg<32>(grid, iters, bg, 0);
+      run_sw64_bg<32>(grid, iters, bg, 1);
+      run_sw64_bg<64>(grid, iters, bg, 1);
+      run_sw64_bg<96>(grid, iters, bg, 1);
+      run_sw64_bg<192>(grid, iters, bg, 1);
+    }
+    return 0;
+  }
   if (argc > 2) {     // operand-major sweep
     run_mn<128, 0, 0>(grid, iters, 16);
     run_mn<128, 1, 0>(grid, iters, 16);

@@ -40,13 +40,14 @@ def main():
         x = torch.randn(N, H, W, ci, device="cuda").bfloat16()
         y = torch.randn(N, d.Ho, d.Wo, co, device="cuda").bfloat16()
         c = torch.randn(N, H, W, ci, device="cuda").bfloat16()
+        mask = torch.randn(N, H, W, ci, device="cuda").bfloat16()      # distinct operand streams, as in the training step
         w = torch.randn(co, ci, r, r) * 0.05
         wf, wd = util.pack(w, lib.BF16)
         stats = torch.zeros(2 * co, dtype=torch.float64, device="cuda")
         sums = torch.zeros(2 * ci, dtype=torch.float64, device="cuda")
         mean = torch.zeros(ci, device="cuda")
         rstd = torch.ones(ci, device="cuda")
-        fuse = lib.BnBwdFuse(c.data_ptr(), c.data_ptr(), mean.data_ptr(), rstd.data_ptr(), sums.data_ptr())
+        fuse = lib.BnBwdFuse(mask.data_ptr(), c.data_ptr(), mean.data_ptr(), rstd.data_ptr(), sums.data_ptr())
 
         def fwd():
             call.svk_conv2d_fwd(d, x.data_ptr(), wf.data_ptr(), y.data_ptr(), stats.data_ptr(), 0, 0, 0, 0, 0, st)

@@ -127,8 +127,12 @@ def test_conv_dgrad_bn_fusion(shape, impl, code):
 
 
 @pytest.mark.parametrize("env", [{"SVK_DISABLE_EPI2": "1"}, {"SVK_DISABLE_WGRAD9": "1", "SVK_DISABLE_WGRADR": "1"},
-                                 {"SVK_DISABLE_PAIR": "1"}, {"SVK_DISABLE_SINGLE_HALO": "1"}],
-                         ids=["first-epilogue-only", "generic-wgrad", "single-cta-late-stages", "three-halo-loads"])
+                                 {"SVK_DISABLE_PAIR": "1"}, {"SVK_DISABLE_SINGLE_HALO": "1"},
+                                 {"SVK_GATHER3_MMA": "1", "SVK_GATHER3_GROUPS": "2", "SVK_GATHER3_STAGES": "6"},
+                                 {"SVK_GATHER3_MMA": "2", "SVK_GATHER3_GROUPS": "3", "SVK_GATHER3_STAGES": "12",
+                                  "SVK_EPI2_MODE": "7", "SVK_EPI2_GROUPS": "3"}],
+                         ids=["first-epilogue-only", "generic-wgrad", "single-cta-late-stages", "three-halo-loads",
+                              "one-issuing-warp", "two-issuing-warps-everywhere"])
 def test_conv_kernel_variants(env):
     """The library picks one kernel variant per shape (measured in the training step); the other variants stay selectable
     through the environment for A/B runs.  The switches are read once per process, so the convolution tests are re-run in a
@@ -142,6 +146,15 @@ def test_conv_kernel_variants(env):
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("ch", [32, 64])
+def test_resident_filter_conv_is_repeatable_at_full_size(ch):
+    """Two MMA-issuing warps, three epilogue groups and six accumulator buffers share one CTA's barriers (conv_tc3.cu): 60
+    back-to-back launches of the training forward and of the fused data gradient at the bench size must reproduce the first
+    launch bit for bit (a barrier whose waiters drift two phases apart shows up here as corrupted tiles or a stalled kernel)."""
+    import stress_conv
+    assert stress_conv.run(ch, 60) == 0
 
 
 @pytest.mark.parametrize("impl,code", [(lib.IMPL_TCGEN05, lib.BF16), (lib.IMPL_SIMT, lib.F32)])
