@@ -165,6 +165,11 @@ conv_tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  if (p.stats && stats_use_mailbox(p)) {       // the CTA's statistics: one atomic per channel and kind (tc_common.cuh)
+    const int n_epi = ((int)blockDim.x - 64) >> 5;
+    if (!p.bn_mask) stats_mailbox_finish(p, scr, 32 * 33, n_epi, BN);
+    else if (p.bn_c) stats_mailbox_finish(p, scr, 32 * SCR_STRIDE, n_epi, p.sub_n ? p.sub_n : BN);
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
@@ -341,6 +346,11 @@ conv_tc_gather2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.stats && stats_use_mailbox(p)) {       // this CTA's statistics (its 128 rows of every pair tile)
+    const int n_epi = ((int)blockDim.x - 64) >> 5;
+    if (!p.bn_mask) stats_mailbox_finish(p, scr, 32 * 33, n_epi, BN);
+    else if (p.bn_c) stats_mailbox_finish(p, scr, 32 * SCR_STRIDE, n_epi, p.sub_n ? p.sub_n : BN);
+  }
   cluster_sync_all();                                       // no CTA leaves while its pair may still signal its barriers
   if (warp == 1) {
     tc_fence_after();

@@ -229,6 +229,11 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.stats && stats_use_mailbox(p)) {       // the CTA's statistics: one atomic per channel and kind (tc_common.cuh)
+    if (q.epi2) gather_epilogue_v2_finish<BN>(p, gbase + q.aux_off, q.n_acc, q.aux_slots, q.aux_nbuf);
+    else if (!p.bn_mask) stats_mailbox_finish(p, scr, 32 * 33, 4 * q.n_acc, BN);
+    else if (p.bn_c) stats_mailbox_finish(p, scr, 32 * SCR_STRIDE, 4 * q.n_acc, BN);
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");

@@ -192,10 +192,28 @@ __device__ __forceinline__ void gather_epilogue_v2(const GatherP& p, const CUten
   if (tid_g == 0) tma_store_wait_all();
   if (stats) {
     if (has_c) { s2a *= coef[512 + 2 * cp]; s2b *= coef[512 + 2 * cp + 1]; }
-    atomicAdd(&p.stats[2 * cp], (double)s1a);
-    atomicAdd(&p.stats[2 * cp + 1], (double)s1b);
-    atomicAdd(&p.stats[p.Nout + 2 * cp], (double)s2a);
-    atomicAdd(&p.stats[p.Nout + 2 * cp + 1], (double)s2b);
+    // mailbox (tc_common.cuh): the group's first aux buffer is free once its last store has completed; thread (cp, rg)
+    // leaves its four partial sums there, gather_epilogue_v2_finish adds them up after the kernel's closing barrier
+    named_bar_sync(bar_id, 128);
+    float* box = reinterpret_cast<float*>(g_aux);
+    *reinterpret_cast<float4*>(box + 4 * tid_g) = make_float4(s1a, s1b, s2a, s2b);
+  }
+}
+
+// After the CTA-wide barrier that follows the role loops: one thread per statistic sums the groups' mailboxes in a fixed
+// order (double) and issues the CTA's single atomic for it.
+template <int BN>
+__device__ __forceinline__ void gather_epilogue_v2_finish(const GatherP& p, const uint8_t* aux, int ngroups, int aux_slots, int nbuf) {
+  constexpr int NP = BN / 2, RG = 128 / NP;
+  const size_t group_bytes = (size_t)nbuf * aux_slots * 128 * BN * 2;
+  for (int ch = threadIdx.x; ch < 2 * BN; ch += blockDim.x) {
+    const int kind = ch / BN, c = ch % BN, cp = c >> 1, e = c & 1;
+    double sum = 0.0;
+    for (int g = 0; g < ngroups; ++g) {
+      const float* box = reinterpret_cast<const float*>(aux + (size_t)g * group_bytes);
+      for (int rg = 0; rg < RG; ++rg) sum += (double)box[4 * (rg * NP + cp) + 2 * kind + e];
+    }
+    if (SVK_DBG_ATOMICS_ON) atomicAdd(&p.stats[kind ? p.Nout + c : c], sum);
   }
 }
 

@@ -2,6 +2,11 @@
 // fprop/dgrad parameter block and epilogue, and the TMA tensor-map builders.
 #pragma once
 #include "svk_common.cuh"
+#if SVK_DBG_NO_STAT_ATOMICS     // diagnostic build: what the statistics atomics at the end of a kernel cost
+#define SVK_DBG_ATOMICS_ON (p.Nout == 12345)
+#else
+#define SVK_DBG_ATOMICS_ON true
+#endif
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -207,6 +212,22 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& r, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
+// ---- statistics of a CTA leave through a "mailbox".  Every epilogue warp used to add its per-channel partial sums to the
+// global fp64 accumulators itself: 8-12 warps x 148 CTAs = 1,200-1,800 same-address atomics per channel, which serialise in L2
+// AFTER the last tile — 5-31 us per launch, ~0.5 ms per training step (tests/time_conv.py with -DSVK_DBG_NO_STAT_ATOMICS=1).
+// Now (one n-block per CTA, i.e. always in ResNet-34) a warp leaves its partials in its own transpose scratch, which it no
+// longer needs, and after the kernel's closing __syncthreads one thread per statistic adds them up in a FIXED order, in
+// double, and issues ONE atomic per CTA (148 per channel).  Box layout: float[2 * bn_eff] — sums of the first kind for the
+// bn_eff channels, then of the second.
+__device__ __forceinline__ bool stats_use_mailbox(const GatherP& p) { return p.n_blocks == 1; }
+__device__ __forceinline__ void stats_mailbox_finish(const GatherP& p, const float* scr, int warp_stride, int n_warps, int bn_eff) {
+  for (int ch = threadIdx.x; ch < 2 * bn_eff; ch += blockDim.x) {
+    double sum = 0.0;
+    for (int w = 0; w < n_warps; ++w) sum += (double)scr[(size_t)w * warp_stride + ch];
+    if (SVK_DBG_ATOMICS_ON) atomicAdd(&p.stats[ch < bn_eff ? ch : p.Nout + (ch - bn_eff)], sum);
+  }
+}
+
 // Epilogue operands of one (pixel row, 32-channel chunk), as loaded: a = additive tensor (res or res_m), b = a mask tensor
 // (the mask of res_m, else bn_mask), c = bn_c.  They are fetched one or two chunks AHEAD of their use so that the global
 // load latency overlaps the MMAs / the previous chunk instead of stalling the 4 epilogue warps once per chunk.
@@ -246,8 +267,8 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
         if (stat_blk >= 0) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
-            atomicAdd(&p.stats[stat_blk * BN + c * 32 + chl], (double)s1[c]);
-            atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + chl], (double)s2[c]);
+            if (SVK_DBG_ATOMICS_ON) atomicAdd(&p.stats[stat_blk * BN + c * 32 + chl], (double)s1[c]);
+            if (SVK_DBG_ATOMICS_ON) atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + chl], (double)s2[c]);
             s1[c] = 0.f; s2[c] = 0.f;
           }
         }
@@ -358,11 +379,15 @@ __device__ __forceinline__ void gather_epilogue(const GatherP& p, uint32_t tmem_
       acc += astep;
       if (acc >= n_tm) { acc -= n_tm; aph ^= 1u; }
     }
-    if (p.stats && stat_blk >= 0) {
+    if (p.stats && stats_use_mailbox(p)) {
+      __syncwarp();                         // the last column pass has read this warp's scratch
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) { myscr[c * 32 + chl] = s1[c]; myscr[BN + c * 32 + chl] = s2[c]; }
+    } else if (p.stats && stat_blk >= 0) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        atomicAdd(&p.stats[stat_blk * BN + c * 32 + chl], (double)s1[c]);
-        atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + chl], (double)s2[c]);
+        if (SVK_DBG_ATOMICS_ON) atomicAdd(&p.stats[stat_blk * BN + c * 32 + chl], (double)s1[c]);
+        if (SVK_DBG_ATOMICS_ON) atomicAdd(&p.stats[p.Nout + stat_blk * BN + c * 32 + chl], (double)s2[c]);
       }
     }
     if (prof) prof_flush(p.prof, 6, clock64() - pt0, pw, lane);
@@ -438,7 +463,13 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
     };
 
     int tile = SPLIT ? (int)blockIdx.x : (int)(blockIdx.x + group * gridDim.x);
-    if (tile >= p.total_tiles) return;
+    const int bn_eff = p.sub_n ? p.sub_n : BN;            // statistics channels of this CTA
+    float* box = reinterpret_cast<float*>(myscr);
+    if (tile >= p.total_tiles) {
+      if (pc && stats_use_mailbox(p))
+        for (int e = lane; e < 2 * bn_eff; e += 32) box[e] = 0.f;
+      return;
+    }
     EpiTile cur = tile_info(tile), nxt = cur;
     EpiAux aux[DEPTH];
     issue(aux[0], cur, 0);
@@ -450,8 +481,8 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             const int sch = p.sub_n ? (((c_first + c) * 32) & (p.sub_n - 1)) + lane : stat_blk * BN + (c_first + c) * 32 + lane;
-            atomicAdd(&p.stats[sch], (double)s1[c]);
-            atomicAdd(&p.stats[p.Nout + sch], (double)s2[c]);
+            if (SVK_DBG_ATOMICS_ON) atomicAdd(&p.stats[sch], (double)s1[c]);
+            if (SVK_DBG_ATOMICS_ON) atomicAdd(&p.stats[p.Nout + sch], (double)s2[c]);
             s1[c] = 0.f; s2[c] = 0.f;
           }
         }
@@ -538,12 +569,22 @@ __device__ __forceinline__ void gather_epilogue_bn(const GatherP& p, uint32_t tm
       if (acc >= n_tm) { acc -= n_tm; aph ^= 1u; }
       cur = nxt;
     }
-    if (pc && stat_blk >= 0) {
+    if (pc && stats_use_mailbox(p)) {
+      __syncwarp();
+      for (int e = lane; e < 2 * bn_eff; e += 32) box[e] = 0.f;      // a SPLIT warp only has half of the chunks
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {         // column-pair mode: two chunks of this lane can be the same channel
+        const int sch = p.sub_n ? (((c_first + c) * 32) & (p.sub_n - 1)) + lane : (c_first + c) * 32 + lane;
+        box[sch] += s1[c];
+        box[bn_eff + sch] += s2[c];
+      }
+    } else if (pc && stat_blk >= 0) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int sch = p.sub_n ? (((c_first + c) * 32) & (p.sub_n - 1)) + lane : stat_blk * BN + (c_first + c) * 32 + lane;
-        atomicAdd(&p.stats[sch], (double)s1[c]);
-        atomicAdd(&p.stats[p.Nout + sch], (double)s2[c]);
+        if (SVK_DBG_ATOMICS_ON) atomicAdd(&p.stats[sch], (double)s1[c]);
+        if (SVK_DBG_ATOMICS_ON) atomicAdd(&p.stats[p.Nout + sch], (double)s2[c]);
       }
     }
     if (prof) prof_flush(p.prof, 6, clock64() - pt0, pw, lane);

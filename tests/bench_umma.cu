@@ -315,8 +315,8 @@ void run_sw64(int grid, int iters) {
 // kernel: warp 1 streams bulk copies global -> shared (two 8 KB copies in flight, back to back) when bg & 1, warps 2-3 do the
 // epilogue-like row writes / column reads when bg & 2.  A_SHIFT: the A descriptor of UMMA pair s starts (s % 3) * 8 rows into
 // the stage (tap offsets of a halo tile).  Reports cycles per UMMA and the bytes the background copies delivered per cycle.
-template <int N>
-__global__ void __launch_bounds__(128, 1) umma_rate_sw64_bg_kernel(int iters, int bg, int a_shift, int commit_every, int tile_len,
+template <int N, int commit_every = 0, int tile_len = 0, int WAIT = 0>
+__global__ void __launch_bounds__(128, 1) umma_rate_sw64_bg_kernel(int iters, int bg, int a_shift,
                                                                     const uint8_t* __restrict__ src, Result* res) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_sw64_bg_kernel(int iters, in
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ __align__(8) uint64_t bar_ld[2];
   __shared__ __align__(8) uint64_t bar_dummy;
+  __shared__ __align__(8) uint64_t bar_ready;
   __shared__ uint32_t tmem_ptr;
   __shared__ volatile int stop_flag;
   __shared__ float hammer_buf[2 * 32 * 36];
@@ -334,6 +335,8 @@ __global__ void __launch_bounds__(128, 1) umma_rate_sw64_bg_kernel(int iters, in
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_ld[0])), "r"(1));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_ld[1])), "r"(1));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_dummy)), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_ready)), "r"(1));
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_ready)) : "memory");   // phase 0 complete
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     stop_flag = 0;
   }
@@ -360,13 +363,23 @@ __global__ void __launch_bounds__(128, 1) umma_rate_sw64_bg_kernel(int iters, in
         const uint64_t a0 = make_desc(base + s * 10240 + (a_shift ? (s % 3) * 512 : 0), 16, 512, 4);
         const uint64_t b0 = make_desc(base + 81920 + (s & 3) * (N * 64), 16, 512, 4);
 #pragma unroll
+        bool early_ok = false;
+        if (WAIT >= 4) early_ok = mbar_try(smem_u32(&bar_ready), 0);
         for (int k = 0; k < 2; ++k) {
           tc_mma<1>(tmem_base + (tile_len ? (uint32_t)(((cnt / tile_len) & 1) * N) : 0u), a0 + 2 * k, b0 + 2 * k, idesc,
                     (tile_len && cnt % tile_len == 0) ? 0u : accum);
           accum = 1; ++cnt;
         }
-        // commit_every UMMAs: a tcgen05.commit to a barrier nobody waits on (the stage-free / tile-done signals of a pipeline)
-        if (commit_every && cnt % commit_every == 0) tc_commit<1>(smem_u32(&bar_dummy));
+        // commit_every UMMAs: a tcgen05.commit to a barrier nobody waits on (the stage-free / tile-done signals of a pipeline);
+        // WAIT: also poll an already-completed barrier + tcgen05.fence first, as a pipeline's "stage full" wait does
+        if (commit_every && cnt % commit_every == 0) {
+          tc_commit<1>(smem_u32(&bar_dummy));
+          // WAIT 1: poll + fence, 2: poll only, 3: fence only, 4: the poll was issued BEFORE this group's MMAs (below) and is only
+          // consumed here, + fence; 5: as 4 without the fence
+          if (WAIT == 1 || WAIT == 2) mbar_wait(smem_u32(&bar_ready), 0);
+          if (WAIT == 4 || WAIT == 5) { if (!early_ok) mbar_wait(smem_u32(&bar_ready), 0); }
+          if (WAIT == 1 || WAIT == 3 || WAIT == 4) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
       }
     }
     tc_commit<1>(smem_u32(&bar_done));
@@ -417,20 +430,20 @@ __global__ void __launch_bounds__(128, 1) umma_rate_sw64_bg_kernel(int iters, in
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
 }
-template <int N>
-void run_sw64_bg(int grid, int iters, int bg, int a_shift, int commit_every = 0, int tile_len = 0) {
+template <int N, int commit_every = 0, int tile_len = 0, int WAIT = 0>
+void run_sw64_bg(int grid, int iters, int bg, int a_shift) {
   const int smem = 81920 + 4 * N * 64 + 16384 + 1024;
-  CK(cudaFuncSetAttribute(umma_rate_sw64_bg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(umma_rate_sw64_bg_kernel<N, commit_every, tile_len, WAIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   Result* d; CK(cudaMalloc(&d, sizeof(Result) * grid)); CK(cudaMemset(d, 0, sizeof(Result) * grid));
   uint8_t* src; CK(cudaMalloc(&src, (size_t)grid * 65536)); CK(cudaMemset(src, 0, (size_t)grid * 65536));
-  for (int rep = 0; rep < 2; ++rep) { CK(cudaMemset(d, 0, sizeof(Result) * grid)); umma_rate_sw64_bg_kernel<N><<<grid, 128, smem>>>(iters, bg, a_shift, commit_every, tile_len, src, d); CK(cudaDeviceSynchronize()); }
+  for (int rep = 0; rep < 2; ++rep) { CK(cudaMemset(d, 0, sizeof(Result) * grid)); umma_rate_sw64_bg_kernel<N, commit_every, tile_len, WAIT><<<grid, 128, smem>>>(iters, bg, a_shift, src, d); CK(cudaDeviceSynchronize()); }
   std::vector<Result> h(grid); CK(cudaMemcpy(h.data(), d, sizeof(Result) * grid, cudaMemcpyDeviceToHost));
   double cyc = 0, bytes = 0; int to = 0;
   for (int i = 0; i < grid; ++i) { cyc += h[i].cycles; bytes += h[i].ns; to += h[i].timeout; }
   cyc /= grid; bytes /= grid;
   const double n_umma = (double)iters * 16;
-  printf("SW64 M=128 N=%3d bulk-copy=%d hammer=%d tap-shift=%d commit-every=%2d tile=%2d : %7.1f cycles/UMMA  %6.1f MAC/clk/SM  copies %5.1f B/clk  timeout=%d\n", N,
-         bg & 1, (bg >> 1) & 1, a_shift, commit_every, tile_len, cyc / n_umma, n_umma * 128.0 * N * 16.0 / cyc, bytes / cyc, to);
+  printf("SW64 M=128 N=%3d bulk-copy=%d hammer=%d tap-shift=%d commit-every=%2d tile=%2d wait=%d : %7.1f cycles/UMMA  %6.1f MAC/clk/SM  copies %5.1f B/clk  timeout=%d\n", N,
+         bg & 1, (bg >> 1) & 1, a_shift, commit_every, tile_len, WAIT, cyc / n_umma, n_umma * 128.0 * N * 16.0 / cyc, bytes / cyc, to);
   fflush(stdout);
   CK(cudaFree(d)); CK(cudaFree(src));
 }
@@ -493,11 +506,16 @@ int main(int argc, char** argv) {
   const int grid = sms & ~1;
   const int iters = argc > 1 ? atoi(argv[1]) : 512;
   printf("SMs %d, %d UMMAs per CTA per launch\n", sms, iters * 4 * 4);
-  if (argc > 4) {     // cost of tcgen05.commit / of starting a new accumulator inside the instruction stream
-    for (int ce : {0, 18, 6, 2}) run_sw64_bg<32>(grid, iters, 0, 1, ce, 0);
-    for (int ce : {0, 18, 6}) run_sw64_bg<32>(grid, iters, 0, 1, ce, 18);
-    for (int ce : {0, 6}) run_sw64_bg<64>(grid, iters, 0, 1, ce, 18);
-    for (int ce : {0, 6}) run_sw64_bg<96>(grid, iters, 0, 1, ce, 6);
+  if (argc > 4) {     // cost of tcgen05.commit / of a (satisfied) barrier wait / of the tcgen05 fence inside the instruction stream
+    run_sw64_bg<32, 0, 0, 0>(grid, iters, 0, 1);
+    run_sw64_bg<32, 2, 0, 0>(grid, iters, 0, 1);
+    run_sw64_bg<32, 2, 0, 1>(grid, iters, 0, 1);
+    run_sw64_bg<32, 2, 0, 2>(grid, iters, 0, 1);
+    run_sw64_bg<32, 2, 0, 3>(grid, iters, 0, 1);
+    run_sw64_bg<32, 2, 0, 4>(grid, iters, 0, 1);
+    run_sw64_bg<32, 2, 0, 5>(grid, iters, 0, 1);
+    run_sw64_bg<128, 2, 0, 1>(grid, iters, 0, 1);
+    run_sw64_bg<128, 2, 0, 5>(grid, iters, 0, 1);
     return 0;
   }
   if (argc > 3) {     // SWIZZLE_64B operands under shared-memory-port contention (stage-1 conv configuration)
