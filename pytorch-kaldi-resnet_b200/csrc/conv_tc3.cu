@@ -132,7 +132,9 @@ conv_tc_gather3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // floor when descriptors are rebuilt per MMA), so everything is hoisted: a descriptor is base + (byte offset >> 4)
       // in its low 14-bit address field, and all tap offsets are compile-time multiples of loop-invariant registers.
       // Even so one warp needs ~18 SASS instructions (~80 cycles) per UMMA, twice what an N = 32 instruction occupies the
-      // tensor pipe for (tests/bench_umma.cu: 40 cycles), and no background traffic changes that (profiles/r02_conv_notes.md).
+      // tensor pipe for (tests/bench_umma.cu: 40 cycles), and no background traffic changes that (profiles/r02_conv_notes.md);
+      // each of a tile's four barrier polls adds ~100 cycles even when its phase completed long ago (same micro-benchmark).
+      // Polling ahead of need (mbarrier.test_wait before the previous stage's MMAs) was tried: its bookkeeping cost more.
       // With q.n_mma == 2 a SECOND issuing warp (the CTA's last) takes every other tile of the CTA: its own accumulator
       // buffer(s), its own positions in the stage ring; tcgen05.commit only tracks the MMAs of the issuing thread.
       constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
