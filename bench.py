@@ -57,7 +57,9 @@ def ncu_traffic():
         n = sum(k["launches"] for k in ks)
         by = sum(k["dram_MB_per_launch"] * 1e6 * k["launches"] for k in ks)
         pipe = sum(k["tensor_pct_of_elapsed"] * k["time_us"] for k in ks) / sum(k["time_us"] for k in ks)
-        return {"traffic": by / n, "traffic_unit": "DRAM bytes per launch (ncu, %d launches of one step)" % n,
+        return {"traffic": by / n,
+                "traffic_unit": "DRAM bytes per kernel launch (ncu: %d kernel launches of one step; a downsample data gradient "
+                                "is one call of `launches` but three kernels)" % n,
                 "traffic_source": "profiles/r02_ncu_step_metrics.json",
                 "ncu_tensor_pipe_pct_of_elapsed": pipe}
     except (OSError, KeyError, ValueError, ZeroDivisionError):
