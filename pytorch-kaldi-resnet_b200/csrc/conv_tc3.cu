@@ -401,6 +401,12 @@ int svk_conv3x3s1_gather3_tc(const void* in, int N, int Hc, int Wc, int Kc, cons
   q.n_stages = ns;
   q.n_tm = (q.n_mma == 2 && (q.n_acc & 1)) ? 2 * q.n_acc : q.n_acc;
   q.g.n_tm = q.n_tm;
+  // what the kernel's barrier protocol relies on (see its skip_tile): fail here, loudly, rather than corrupt tiles there
+  SVK_REQUIRE(q.n_mma == 1 || ((q.n_tm & 1) == 0 && ns % (2 * (q.single ? 1 : 3)) == 0), SVK_E_UNSUPPORTED,
+              "conv_tc3: two issuing warps need an even number of accumulator buffers (%d) and whole tiles of stages per warp (%d)",
+              q.n_tm, ns);
+  SVK_REQUIRE(q.n_tm <= 8 && q.n_tm * BN <= 512 && ns <= 16 && q.n_tm % q.n_acc == 0, SVK_E_UNSUPPORTED,
+              "conv_tc3: %d accumulator buffers of %d columns / %d stages exceed the kernel's TMEM or barrier tables", q.n_tm, BN, ns);
   const size_t smem = fixed + (size_t)ns * q.a_stage_bytes;
   {
     const size_t auxbar = (size_t)ns * q.a_stage_bytes + w_bytes;
